@@ -1,0 +1,63 @@
+"""In-tree build of libcassie2d.so (sm_100a only): `python -m cassierl_b200.build`.
+
+Replaces the reference's src/Makefile:1-64 (g++ -> bin/libcassie2d.so linking MuJoCo, RBDL,
+qpOASES).  Translation units are compiled in parallel, objects are cached by source mtime.
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "lib", "obj")
+LIB = os.path.join(HERE, "lib", "libcassie2d.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr"]
+UNITS = ["kernels_f32.cu", "kernels_f64.cu", "cassie2d_api.cu", "mjcf_flatten.cpp"]
+
+
+def _deps():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "cassie2d.h")]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _compile(unit, verbose):
+    src = os.path.join(CSRC, unit)
+    obj = os.path.join(OBJ, unit + ".o")
+    if not _stale(obj, _deps()):
+        return obj
+    cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    if unit.endswith(".cpp"):
+        cmd = [NVCC, "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-x", "c++", "-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed on " + unit)
+    return obj
+
+
+def build(verbose=False, force=False):
+    """Compiles every CUDA translation unit for sm_100a and links libcassie2d.so.  Returns its path."""
+    os.makedirs(OBJ, exist_ok=True)
+    if force:
+        for f in os.listdir(OBJ):
+            os.remove(os.path.join(OBJ, f))
+    with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
+        objs = list(ex.map(lambda u: _compile(u, verbose), UNITS))
+    if _stale(LIB, objs):
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart", "static", "-ldl"]
+        subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))

@@ -1,0 +1,470 @@
+// C-ABI of libcassie2d.so (include/cassie2d.h): the reference's ten legacy symbols
+// (CassieRL/cassierl src/Cassie2d/Cassie2d.cpp:15-27) as a batch of one, plus the batch entry
+// points.  Host glue only -- all arithmetic is in the CUDA kernels (env_kernels.cuh).
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <dlfcn.h>
+
+#include "../../include/cassie2d.h"
+#include "batch_state.h"
+#include "mjcf_flatten.h"
+
+namespace cassie {
+static std::atomic<long long> g_launches{0};
+long long kernel_launch_count() { return g_launches.load(); }
+void count_launch() { g_launches.fetch_add(1); }
+}  // namespace cassie
+
+using namespace cassie;
+
+static thread_local std::string g_last_error;
+static int fail(const std::string& msg) {
+  g_last_error = msg;
+  return -1;
+}
+#define CU_OK(expr)                                                                              \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+  } while (0)
+
+// Constructor pose (Cassie2d.cpp:56-58) and Python reset pose (cassie2d.py:79-85) as StateGeneral
+static const double kCtorState26[26] = {0.0, 0.939, 0.0, 0, 0, 0, 0.68111815, -1.40730357, 1.62972042, -1.77611107, -0.61968407,
+                                        0, 0, 0, 0, 0, 0.68111815, -1.40730353, 1.62972043, -1.77611107, -0.61968402,
+                                        0, 0, 0, 0, 0};
+static const double kPyResetState26[26] = {0.0, 0.939, 0.0, 0, 0, 0, 0.68111815, -1.40730357, 1.62972042, -1.77611107, -0.61968407,
+                                           0, 0, 0, 0, 0, 0.68111815, -1.40730357, 1.62972042, -1.77611107, -0.61968407,
+                                           0, 0, 0, 0, 0};
+
+static std::string default_xml_path() {
+  if (const char* e = getenv("CASSIE2D_XML")) return e;
+  Dl_info info;
+  if (dladdr((void*)&default_xml_path, &info) && info.dli_fname) {
+    std::string p = info.dli_fname;  // <pkg>/lib/libcassie2d.so -> <pkg>/model/cassie2d_stiff.xml
+    size_t s = p.rfind('/');
+    if (s != std::string::npos) {
+      p = p.substr(0, s);
+      size_t s2 = p.rfind('/');
+      if (s2 != std::string::npos) return p.substr(0, s2) + "/model/cassie2d_stiff.xml";
+    }
+  }
+  return "cassie2d_stiff.xml";
+}
+
+struct CassieBatch {
+  int n = 0, device = 0, precision = 32;
+  FlatModels models;
+  ModelPair<float> mp32;
+  ModelPair<double> mp64;
+  BatchView<float> v32;
+  BatchView<double> v64;
+  std::vector<void*> allocs;
+  void* scratch_state = nullptr;   // real [26]: single reset state staging (device)
+  // host-variant staging
+  void* d_action = nullptr;        // real [n][7]
+  void* d_obs = nullptr;           // real [n][26]
+  void* d_reward = nullptr;        // real [n]
+  uint8_t* d_done = nullptr;       // [n]
+  void* d_state26 = nullptr;       // real [n][26]
+  void* d_phase = nullptr;         // real [n]
+  double* d_traj = nullptr;
+  cudaStream_t own_stream = nullptr;
+  size_t real_size() const { return precision == 64 ? 8 : 4; }
+};
+
+template <typename T>
+static int alloc_view(CassieBatch* h, BatchView<T>& v) {
+  const size_t n = (size_t)h->n;
+  auto A = [&](void** p, size_t bytes) -> cudaError_t {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) { h->allocs.push_back(*p); e = cudaMemset(*p, 0, bytes); }
+    return e;
+  };
+  v.n = h->n;
+  CU_OK(A((void**)&v.qpos, sizeof(T) * 13 * n));
+  CU_OK(A((void**)&v.qvel, sizeof(T) * 13 * n));
+  CU_OK(A((void**)&v.warm, sizeof(T) * 13 * n));
+  CU_OK(A((void**)&v.op, sizeof(T) * 12 * n));
+  CU_OK(A((void**)&v.clock, sizeof(double) * n));
+  CU_OK(A((void**)&v.jsum0, sizeof(T) * n));
+  CU_OK(A((void**)&v.stats, sizeof(int32_t) * 4 * n));
+  v.traj = nullptr; v.traj_rows = 0; v.traj_tmax = 1.0;
+  CU_OK(A(&h->scratch_state, sizeof(T) * 26));
+  CU_OK(A(&h->d_action, sizeof(T) * 7 * n));
+  CU_OK(A(&h->d_obs, sizeof(T) * 26 * n));
+  CU_OK(A(&h->d_reward, sizeof(T) * n));
+  CU_OK(A((void**)&h->d_done, n));
+  CU_OK(A(&h->d_state26, sizeof(T) * 26 * n));
+  CU_OK(A(&h->d_phase, sizeof(T) * n));
+  return 0;
+}
+
+template <typename T> static ModelPair<T>& MP(CassieBatch* h);
+template <> ModelPair<float>& MP<float>(CassieBatch* h) { return h->mp32; }
+template <> ModelPair<double>& MP<double>(CassieBatch* h) { return h->mp64; }
+template <typename T> static BatchView<T>& BV(CassieBatch* h);
+template <> BatchView<float>& BV<float>(CassieBatch* h) { return h->v32; }
+template <> BatchView<double>& BV<double>(CassieBatch* h) { return h->v64; }
+
+// uploads one StateGeneral (host doubles) into the device scratch in the handle's precision
+template <typename T>
+static int upload_state(CassieBatch* h, const double* s26, cudaStream_t st) {
+  T tmp[26];
+  for (int i = 0; i < 26; i++) tmp[i] = (T)s26[i];
+  CU_OK(cudaMemcpyAsync(h->scratch_state, tmp, sizeof(tmp), cudaMemcpyHostToDevice, st));
+  CU_OK(cudaStreamSynchronize(st));  // tmp is on the stack
+  return 0;
+}
+
+#define DISPATCH(h, CALL)                          \
+  do {                                             \
+    if ((h)->precision == 64) { using R = double; CALL; } \
+    else { using R = float; CALL; }                \
+  } while (0)
+
+static int set_device(const CassieBatch* h) {
+  CU_OK(cudaSetDevice(h->device));
+  return 0;
+}
+
+extern "C" {
+
+const char* CassieGetLastError(void) { return g_last_error.c_str(); }
+long long CassieKernelLaunchCount(void) { return kernel_launch_count(); }
+
+CassieBatch* Cassie2dBatchInit(int n_envs, int device, const char* xml_path, int precision) {
+  g_last_error.clear();
+  if (n_envs <= 0) { fail("n_envs must be positive"); return nullptr; }
+  if (precision != 32 && precision != 64) { fail("precision must be 32 or 64"); return nullptr; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    fail(std::string("no CUDA device (libcassie2d has no CPU path): ") + cudaGetErrorString(e));
+    return nullptr;
+  }
+  if (device < 0 || device >= ndev) { fail("bad device index"); return nullptr; }
+  CassieBatch* h = new CassieBatch();
+  h->n = n_envs; h->device = device; h->precision = precision;
+  std::string err;
+  const std::string path = xml_path && *xml_path ? std::string(xml_path) : default_xml_path();
+  if (!flatten_mjcf_file(path, &h->models, &err)) {
+    fail("model '" + path + "': " + err);
+    delete h;
+    return nullptr;
+  }
+  h->mp32.phys = cast_model<float>(h->models.phys);
+  h->mp32.ctrl = cast_model<float>(h->models.ctrl);
+  h->mp64.phys = h->models.phys;
+  h->mp64.ctrl = h->models.ctrl;
+  if (cudaSetDevice(device) != cudaSuccess) { fail("cudaSetDevice failed"); delete h; return nullptr; }
+  int rc = precision == 64 ? alloc_view<double>(h, h->v64) : alloc_view<float>(h, h->v32);
+  if (rc == 0 && cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) rc = fail("stream create failed");
+  if (rc != 0) { Cassie2dBatchDestroy(h); return nullptr; }
+  // constructor: standing pose, mj_forward, setState (Cassie2d.cpp:56-64)
+  if (Cassie2dBatchReset(h, nullptr, kCtorState26, nullptr) != 0) { Cassie2dBatchDestroy(h); return nullptr; }
+  cudaError_t ce;
+  DISPATCH(h, ce = Launch<R>::refresh_op(MP<R>(h), BV<R>(h), nullptr, nullptr));
+  if (ce != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+    fail(std::string("init launch failed: ") + cudaGetErrorString(ce != cudaSuccess ? ce : cudaGetLastError()));
+    Cassie2dBatchDestroy(h);
+    return nullptr;
+  }
+  return h;
+}
+
+void Cassie2dBatchDestroy(CassieBatch* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->d_traj) cudaFree(h->d_traj);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+int Cassie2dBatchNumEnvs(const CassieBatch* h) { return h ? h->n : -1; }
+int Cassie2dBatchPrecision(const CassieBatch* h) { return h ? h->precision : -1; }
+int Cassie2dBatchDevice(const CassieBatch* h) { return h ? h->device : -1; }
+int Cassie2dBatchRealSize(const CassieBatch* h) { return h ? (int)h->real_size() : -1; }
+
+int Cassie2dBatchReset(CassieBatch* h, const uint8_t* mask_dev, const double* state26_host, void* stream) {
+  if (!h) return fail("null handle");
+  if (set_device(h)) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const double* s = state26_host ? state26_host : kPyResetState26;
+  DISPATCH(h, {
+    if (upload_state<R>(h, s, st)) return -1;
+    CU_OK(Launch<R>::reset(BV<R>(h), (const R*)h->scratch_state, 0, mask_dev, st));
+  });
+  return 0;
+}
+
+int Cassie2dBatchSetState(CassieBatch* h, const void* state26_dev, void* stream) {
+  if (!h || !state26_dev) return fail("null argument");
+  if (set_device(h)) return -1;
+  DISPATCH(h, CU_OK(Launch<R>::reset(BV<R>(h), (const R*)state26_dev, 1, nullptr, (cudaStream_t)stream)));
+  return 0;
+}
+
+int Cassie2dBatchGetGeneralState(CassieBatch* h, void* state26_dev, void* stream) {
+  if (!h || !state26_dev) return fail("null argument");
+  if (set_device(h)) return -1;
+  DISPATCH(h, CU_OK(Launch<R>::get_general(BV<R>(h), (R*)state26_dev, (cudaStream_t)stream)));
+  return 0;
+}
+
+int Cassie2dBatchGetOperationalSpaceState(CassieBatch* h, void* state18_dev, void* stream) {
+  if (!h || !state18_dev) return fail("null argument");
+  if (set_device(h)) return -1;
+  DISPATCH(h, CU_OK(Launch<R>::get_op(BV<R>(h), (R*)state18_dev, (cudaStream_t)stream)));
+  return 0;
+}
+
+int Cassie2dBatchStep(CassieBatch* h, int mode, const void* action_dev, int n_substeps, uint32_t* contact_mask_dev,
+                      void* stream) {
+  if (!h || !action_dev) return fail("null argument");
+  if (mode < 0 || mode > 3) return fail("bad mode");
+  if (n_substeps < 0) return fail("n_substeps < 0");
+  if (set_device(h)) return -1;
+  StepArgs a{mode, n_substeps, action_dev, contact_mask_dev};
+  DISPATCH(h, CU_OK(Launch<R>::step(MP<R>(h), BV<R>(h), a, (cudaStream_t)stream)));
+  return 0;
+}
+
+int Cassie2dBatchEnvStep(CassieBatch* h, int task, int mode, const void* action_dev, int n_substeps, int flags,
+                         void* obs_dev, void* reward_dev, uint8_t* done_dev, void* stream) {
+  if (!h || !action_dev || !obs_dev || !reward_dev || !done_dev) return fail("null argument");
+  if (task != 0 && task != 1) return fail("bad task");
+  if (mode != 0 && mode != 1 && mode != 3) return fail("bad mode (the Python envs offer Torque, PD, OSC)");
+  if (n_substeps < 0) return fail("n_substeps < 0");
+  if (task == 1 && !h->d_traj) return fail("imitation task needs Cassie2dBatchSetTrajectory first");
+  if (set_device(h)) return -1;
+  EnvStepArgs a{task, mode, n_substeps, flags, action_dev, obs_dev, reward_dev, done_dev};
+  DISPATCH(h, CU_OK(Launch<R>::env_step(MP<R>(h), BV<R>(h), a, (cudaStream_t)stream)));
+  return 0;
+}
+
+int Cassie2dBatchEnvReset(CassieBatch* h, int task, int flags, void* obs_dev, void* stream) {
+  if (!h) return fail("null handle");
+  if (task == 1 && !h->d_traj) return fail("imitation task needs Cassie2dBatchSetTrajectory first");
+  if (set_device(h)) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH(h, {
+    if (upload_state<R>(h, kPyResetState26, st)) return -1;
+    CU_OK(Launch<R>::env_reset(MP<R>(h), BV<R>(h), task, flags, (const R*)h->scratch_state, (R*)obs_dev, st));
+  });
+  return 0;
+}
+
+int Cassie2dBatchSetTrajectory(CassieBatch* h, const double* qpos_rows_host, int n_rows, double t_max) {
+  if (!h || !qpos_rows_host || n_rows <= 0 || !(t_max > 0)) return fail("bad trajectory");
+  if (set_device(h)) return -1;
+  CU_OK(cudaDeviceSynchronize());
+  if (h->d_traj) cudaFree(h->d_traj);
+  CU_OK(cudaMalloc((void**)&h->d_traj, sizeof(double) * 13 * (size_t)n_rows));
+  CU_OK(cudaMemcpy(h->d_traj, qpos_rows_host, sizeof(double) * 13 * (size_t)n_rows, cudaMemcpyHostToDevice));
+  h->v32.traj = h->v64.traj = h->d_traj;
+  h->v32.traj_rows = h->v64.traj_rows = n_rows;
+  h->v32.traj_tmax = h->v64.traj_tmax = t_max;
+  return 0;
+}
+
+int Cassie2dBatchSquat(CassieBatch* h, int mode, int n_steps, const void* phase_dev, uint32_t* contact_mask_dev,
+                       void* stream) {
+  if (!h) return fail("null handle");
+  if (mode != 2 && mode != 3) return fail("squat mode must be JACOBIAN or OSC");
+  if (n_steps < 0) return fail("n_steps < 0");
+  if (set_device(h)) return -1;
+  SquatArgs a{mode, n_steps, phase_dev, contact_mask_dev};
+  DISPATCH(h, CU_OK(Launch<R>::squat(MP<R>(h), BV<R>(h), a, (cudaStream_t)stream)));
+  return 0;
+}
+
+int Cassie2dBatchGetStats(CassieBatch* h, int32_t* stats_dev, void* stream) {
+  if (!h || !stats_dev) return fail("null argument");
+  if (set_device(h)) return -1;
+  const int32_t* src = h->precision == 64 ? h->v64.stats : h->v32.stats;
+  // stored [4][n] -> returned [n][4]
+  std::vector<int32_t> tmp(4 * (size_t)h->n), out(4 * (size_t)h->n);
+  CU_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  CU_OK(cudaMemcpy(tmp.data(), src, tmp.size() * 4, cudaMemcpyDeviceToHost));
+  for (int e = 0; e < h->n; e++)
+    for (int k = 0; k < 4; k++) out[(size_t)e * 4 + k] = tmp[(size_t)k * h->n + e];
+  CU_OK(cudaMemcpy(stats_dev, out.data(), out.size() * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int Cassie2dBatchSync(CassieBatch* h) {
+  if (!h) return fail("null handle");
+  if (set_device(h)) return -1;
+  CU_OK(cudaDeviceSynchronize());
+  return 0;
+}
+
+// ---- host-buffer variants: H2D + launch + D2H + sync on the handle's own stream
+int Cassie2dBatchStepHost(CassieBatch* h, int mode, const void* action_host, int n_substeps, void* state26_host) {
+  if (!h || !action_host) return fail("null argument");
+  if (mode < 0 || mode > 3) return fail("bad mode");
+  if (set_device(h)) return -1;
+  const size_t rs = h->real_size(), adim = mode == 3 ? 7 : 6;
+  cudaStream_t st = h->own_stream;
+  CU_OK(cudaMemcpyAsync(h->d_action, action_host, rs * adim * h->n, cudaMemcpyHostToDevice, st));
+  if (Cassie2dBatchStep(h, mode, h->d_action, n_substeps, nullptr, st)) return -1;
+  if (state26_host) {
+    if (Cassie2dBatchGetGeneralState(h, h->d_state26, st)) return -1;
+    CU_OK(cudaMemcpyAsync(state26_host, h->d_state26, rs * 26 * h->n, cudaMemcpyDeviceToHost, st));
+  }
+  CU_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int Cassie2dBatchEnvStepHost(CassieBatch* h, int task, int mode, const void* action_host, int n_substeps, int flags,
+                             void* obs_host, void* reward_host, uint8_t* done_host) {
+  if (!h || !action_host || !obs_host || !reward_host || !done_host) return fail("null argument");
+  if (mode != 0 && mode != 1 && mode != 3) return fail("bad mode (the Python envs offer Torque, PD, OSC)");
+  if (set_device(h)) return -1;
+  const size_t rs = h->real_size(), adim = mode == 3 ? 7 : 6, odim = task == 1 ? 26 : 17;
+  cudaStream_t st = h->own_stream;
+  CU_OK(cudaMemcpyAsync(h->d_action, action_host, rs * adim * h->n, cudaMemcpyHostToDevice, st));
+  if (Cassie2dBatchEnvStep(h, task, mode, h->d_action, n_substeps, flags, h->d_obs, h->d_reward, h->d_done, st)) return -1;
+  CU_OK(cudaMemcpyAsync(obs_host, h->d_obs, rs * odim * h->n, cudaMemcpyDeviceToHost, st));
+  CU_OK(cudaMemcpyAsync(reward_host, h->d_reward, rs * h->n, cudaMemcpyDeviceToHost, st));
+  CU_OK(cudaMemcpyAsync(done_host, h->d_done, (size_t)h->n, cudaMemcpyDeviceToHost, st));
+  CU_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int Cassie2dBatchSquatHost(CassieBatch* h, int mode, int n_steps, const void* phase_host, void* state26_host) {
+  if (!h) return fail("null handle");
+  if (set_device(h)) return -1;
+  const size_t rs = h->real_size();
+  cudaStream_t st = h->own_stream;
+  if (phase_host) CU_OK(cudaMemcpyAsync(h->d_phase, phase_host, rs * h->n, cudaMemcpyHostToDevice, st));
+  if (Cassie2dBatchSquat(h, mode, n_steps, phase_host ? h->d_phase : nullptr, nullptr, st)) return -1;
+  if (state26_host) {
+    if (Cassie2dBatchGetGeneralState(h, h->d_state26, st)) return -1;
+    CU_OK(cudaMemcpyAsync(state26_host, h->d_state26, rs * 26 * h->n, cudaMemcpyDeviceToHost, st));
+  }
+  CU_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ------------------------------------------------------------------ FP32 peak probe
+}  // extern "C"
+
+__global__ void __launch_bounds__(256) k_fp32_probe(float* out, int iters) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float b = 0.9999f, c = 1e-4f;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+      a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" {
+
+double CassieMeasureFp32Peak(int device) {
+  if (cudaSetDevice(device) != cudaSuccess) { fail("cudaSetDevice failed"); return -1.0; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { fail("no device properties"); return -1.0; }
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  float* out = nullptr;
+  if (cudaMalloc((void**)&out, sizeof(float) * blocks * threads) != cudaSuccess) { fail("cudaMalloc failed"); return -1.0; }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0);
+    k_fp32_probe<<<blocks, threads>>>(out, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  return best;
+}
+
+// ------------------------------------------------------------------ legacy one-env ABI
+// Cassie2d.cpp:15-27.  The handle is a batch of one in fp64 (the reference computes in double).
+struct Cassie2d {
+  CassieBatch* b;
+  bool display;
+  double* pinned;  // 26 doubles staging
+};
+
+static void legacy_die(const char* what) {
+  // the reference aborts through mju_error_s on fatal errors (Cassie2d.cpp:49-52)
+  fprintf(stderr, "libcassie2d: %s: %s\n", what, g_last_error.c_str());
+  abort();
+}
+
+Cassie2d* Cassie2dInit(void) {
+  int dev = 0;
+  if (const char* e = getenv("CASSIE2D_DEVICE")) dev = atoi(e);
+  int prec = 64;
+  if (const char* e = getenv("CASSIE2D_LEGACY_PRECISION")) prec = atoi(e);
+  CassieBatch* b = Cassie2dBatchInit(1, dev, nullptr, prec);
+  if (!b) legacy_die("Cassie2dInit");
+  Cassie2d* c = new Cassie2d();
+  c->b = b;
+  c->display = false;
+  if (cudaMallocHost((void**)&c->pinned, sizeof(double) * 32) != cudaSuccess) legacy_die("Cassie2dInit(pinned)");
+  return c;
+}
+
+static void legacy_step(Cassie2d* c, int mode, const double* act, int adim) {
+  CassieBatch* b = c->b;
+  if (b->precision == 64) {
+    memcpy(c->pinned, act, sizeof(double) * adim);
+  } else {
+    float* f = (float*)c->pinned;
+    for (int i = 0; i < adim; i++) f[i] = (float)act[i];
+  }
+  if (Cassie2dBatchStepHost(b, mode, c->pinned, 1, nullptr)) legacy_die("Step");
+}
+
+void Reset(Cassie2d* c, StateGeneral* state) {
+  if (Cassie2dBatchReset(c->b, nullptr, (const double*)state, c->b->own_stream) || cudaStreamSynchronize(c->b->own_stream) != cudaSuccess)
+    legacy_die("Reset");
+}
+void StepOsc(Cassie2d* c, ControllerOsc* a) { legacy_step(c, CASSIE_MODE_OSC, (const double*)a, 7); }
+void StepTorque(Cassie2d* c, ControllerTorque* a) { legacy_step(c, CASSIE_MODE_TORQUE, a->torques, 6); }
+void StepJacobian(Cassie2d* c, ControllerForce* a) { legacy_step(c, CASSIE_MODE_JACOBIAN, (const double*)a, 6); }
+void StepPd(Cassie2d* c, ControllerPd* a) { legacy_step(c, CASSIE_MODE_PD, a->angles, 6); }
+
+static void legacy_read(Cassie2d* c, bool op, double* out, int count) {
+  CassieBatch* b = c->b;
+  cudaStream_t st = b->own_stream;
+  int rc = op ? Cassie2dBatchGetOperationalSpaceState(b, b->d_state26, st) : Cassie2dBatchGetGeneralState(b, b->d_state26, st);
+  if (rc || cudaMemcpyAsync(c->pinned, b->d_state26, b->real_size() * count, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess)
+    legacy_die("GetState");
+  if (b->precision == 64) memcpy(out, c->pinned, sizeof(double) * count);
+  else for (int i = 0; i < count; i++) out[i] = (double)((float*)c->pinned)[i];
+}
+void GetGeneralState(Cassie2d* c, StateGeneral* s) { legacy_read(c, false, (double*)s, 26); }
+void GetOperationalSpaceState(Cassie2d* c, StateOperationalSpace* s) {
+  // the reference leaves left_x[2], left_xd[2], right_x[2], right_xd[2] untouched
+  // (Cassie2d.cpp:226-235); keep whatever the caller had there
+  double o[18];
+  legacy_read(c, true, o, 18);
+  double* d = (double*)s;
+  for (int i = 0; i < 18; i++)
+    if (!(i == 8 || i == 11 || i == 14 || i == 17)) d[i] = o[i];
+}
+void Display(Cassie2d* c, bool display) { if (c) c->display = display; }
+void Render(Cassie2d*) {}
+
+}  // extern "C"

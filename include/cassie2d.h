@@ -1,0 +1,159 @@
+/* libcassie2d -- B200-native drop-in for CassieRL/cassierl's bin/libcassie2d.so.
+ *
+ * Part 1 (legacy ABI) is byte-compatible with the ten extern "C" symbols of the reference
+ * (src/Cassie2d/Cassie2d.cpp:15-27) and its POD structs (src/Cassie2d/RobotInterface.h:14-50,
+ * mirrored by rllab/envs/cassie2d_structs.py:5-51): one env per handle, host structs,
+ * synchronous.  The unmodified ctypes wrappers rllab/envs/cassie2d.py:22-50 and
+ * cassie_stand2d.py:20-48 bind these symbols as they are.
+ *
+ * Part 2 (batch ABI) is the same operator set over a batch dimension: N independent envs per
+ * handle, state resident in HBM, one fused CUDA launch per call.  The reference defines no
+ * batch interface; each entry point cites the legacy call it generalises.
+ *
+ * All entry points are plain C: pointers, sizes, ints.  No CUDA or torch types appear; a
+ * stream is passed as void* (cudaStream_t, NULL = the legacy default stream).
+ * There is no CPU fallback: every call fails (batch: returns < 0, legacy: aborts like the
+ * reference's mju_error, Cassie2d.cpp:49-52) when no CUDA device is usable.
+ */
+#ifndef CASSIE2D_H_
+#define CASSIE2D_H_
+
+#include <stdint.h>
+#ifndef __cplusplus
+#include <stdbool.h>
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ Part 1: legacy ABI */
+
+/* RobotInterface.h:14-50 -- all double, no padding */
+typedef struct { double torques[6]; } ControllerTorque;                      /* :14-16 */
+typedef struct { double left_force[3]; double right_force[3]; } ControllerForce; /* :18-21  (Fx, Fz, My) */
+typedef struct { double body_xdd[2]; double left_xdd[2]; double right_xdd[2]; double pitch_add; } ControllerOsc; /* :23-28 */
+typedef struct { double angles[6]; } ControllerPd;                           /* :30-32 */
+typedef struct {                                                             /* :34-41 */
+  double base_pos[3]; double base_vel[3];
+  double left_pos[5]; double left_vel[5];
+  double right_pos[5]; double right_vel[5];
+} StateGeneral;
+typedef struct {                                                             /* :43-50 */
+  double body_x[3]; double body_xd[3];
+  double left_x[3]; double left_xd[3];
+  double right_x[3]; double right_xd[3];
+} StateOperationalSpace;
+
+typedef struct Cassie2d Cassie2d;
+
+Cassie2d* Cassie2dInit(void);                                          /* Cassie2d.cpp:17 */
+void Reset(Cassie2d* cassie, StateGeneral* state);                     /* :18 */
+void StepOsc(Cassie2d* cassie, ControllerOsc* action);                 /* :19 */
+void StepTorque(Cassie2d* cassie, ControllerTorque* action);           /* :20 */
+void StepJacobian(Cassie2d* cassie, ControllerForce* action);          /* :21 */
+void StepPd(Cassie2d* cassie, ControllerPd* action);                   /* :22 */
+void GetGeneralState(Cassie2d* cassie, StateGeneral* state);           /* :23 */
+void GetOperationalSpaceState(Cassie2d* cassie, StateOperationalSpace* state); /* :24 */
+void Display(Cassie2d* cassie, bool display);                          /* :25 (no-op: no viewer) */
+void Render(Cassie2d* cassie);                                         /* :26 (no-op; tolerant of a
+                                                                          truncated handle, the Python
+                                                                          wrapper declares no argtypes) */
+
+/* ------------------------------------------------------------------ Part 2: batch ABI */
+
+typedef struct CassieBatch CassieBatch;
+
+enum { CASSIE_F32 = 32, CASSIE_F64 = 64 };
+/* control mode of a step: which legacy Step* it batches */
+enum { CASSIE_MODE_TORQUE = 0,   /* StepTorque   Cassie2d.cpp:86-94,   action dim 6 */
+       CASSIE_MODE_PD = 1,       /* StepPd       Cassie2d.cpp:96-117,  action dim 6 */
+       CASSIE_MODE_JACOBIAN = 2, /* StepJacobian Cassie2d.cpp:119-177, action dim 6 */
+       CASSIE_MODE_OSC = 3 };    /* StepOsc      Cassie2d.cpp:179-209, action dim 7 */
+/* task (observation / reward / termination of the Python env) */
+enum { CASSIE_TASK_STAND = 0,    /* rllab/envs/cassie_stand2d.py:86-137: 17-d obs */
+       CASSIE_TASK_IMITATE = 1 };/* rllab/envs/cassie2d.py:97-225:       26-d obs */
+/* flags of Cassie2dBatchEnvStep */
+enum { CASSIE_AUTO_RESET = 1,        /* done envs are reset to the standing pose (cassie2d.py:78-88) */
+       CASSIE_FRESH_OBS_ON_RESET = 2,/* fix SURVEY App. D.2: recompute the lagged op-space state on reset */
+       CASSIE_LIVE_QSTATE = 4 };     /* fix SURVEY App. D.4: imitation reward reads the live joint angles */
+
+/* Last error message of the calling thread ("" if none). */
+const char* CassieGetLastError(void);
+
+/* Creates n_envs envs on CUDA device `device`, all at the constructor's standing pose
+ * (Cassie2d.cpp:56-64).  xml_path NULL = the packaged cassie2d_stiff.xml (env CASSIE2D_XML
+ * overrides).  precision = CASSIE_F32 | CASSIE_F64.  Returns NULL on failure. */
+CassieBatch* Cassie2dBatchInit(int n_envs, int device, const char* xml_path, int precision);
+void Cassie2dBatchDestroy(CassieBatch* h);
+int Cassie2dBatchNumEnvs(const CassieBatch* h);
+int Cassie2dBatchPrecision(const CassieBatch* h);
+int Cassie2dBatchDevice(const CassieBatch* h);
+/* bytes of one real (4 or 8): every `real` buffer below has the handle's precision */
+int Cassie2dBatchRealSize(const CassieBatch* h);
+
+/* Reset (Cassie2d.cpp:78-82): writes qpos/qvel of the envs whose mask byte is non-zero
+ * (mask NULL = all).  state26 = one StateGeneral in memory order (host pointer, 26 doubles;
+ * NULL = the Python reset pose, cassie2d.py:79-85).  As in the reference, time, solver warm
+ * start and the lagged op-space state are NOT touched.  mask is a DEVICE pointer [n]. */
+int Cassie2dBatchReset(CassieBatch* h, const uint8_t* mask_dev, const double* state26_host, void* stream);
+/* per-env states: DEVICE pointer, real [n][26] in StateGeneral memory order */
+int Cassie2dBatchSetState(CassieBatch* h, const void* state26_dev, void* stream);
+/* GetGeneralState (Cassie2d.cpp:213-216): DEVICE pointer, real [n][26] */
+int Cassie2dBatchGetGeneralState(CassieBatch* h, void* state26_dev, void* stream);
+/* GetOperationalSpaceState (Cassie2d.cpp:218-237): DEVICE pointer, real [n][18] */
+int Cassie2dBatchGetOperationalSpaceState(CassieBatch* h, void* state18_dev, void* stream);
+
+/* n_substeps consecutive legacy Step* calls with the same action (the Python envs' inner
+ * loop, cassie2d.py:115-122).  action: DEVICE pointer, real [n][action_dim(mode)].
+ * contact_mask_dev (optional, DEVICE uint32 [n]): floor-contact bit mask of the LAST substep
+ * (bit 2g+e: geom g of the MJCF file, capsule end e). */
+int Cassie2dBatchStep(CassieBatch* h, int mode, const void* action_dev, int n_substeps,
+                      uint32_t* contact_mask_dev, void* stream);
+
+/* One policy step of the Python env for every env, fused in one launch: n_substeps Step*,
+ * observation, reward, termination, optional auto-reset.
+ *   obs_dev    real [n][17] (stand) or [n][26] (imitate)     reward_dev real [n]
+ *   done_dev   uint8 [n]                                     (all DEVICE pointers) */
+int Cassie2dBatchEnvStep(CassieBatch* h, int task, int mode, const void* action_dev, int n_substeps,
+                         int flags, void* obs_dev, void* reward_dev, uint8_t* done_dev, void* stream);
+/* env.reset() observation of every env (stale op-space state as in the reference unless
+ * CASSIE_FRESH_OBS_ON_RESET): resets all envs to the standing pose, zeroes episode clocks. */
+int Cassie2dBatchEnvReset(CassieBatch* h, int task, int flags, void* obs_dev, void* stream);
+/* reference trajectory table for CASSIE_TASK_IMITATE: host pointer, [n_rows][13] doubles =
+ * Cassie2dTraj.qpos (cassie2d_trajectory.py:31-134), plus t_max = time[-1] and the row count
+ * used by state(t) (:16-19). */
+int Cassie2dBatchSetTrajectory(CassieBatch* h, const double* qpos_rows_host, int n_rows, double t_max);
+
+/* The squatting.py loop (squatting.py:8-16) on device: n_steps iterations of
+ * standing_controller_jacobian (mode JACOBIAN, cassie2d.py:297-331) or
+ * standing_controller_osc (mode OSC, cassie2d.py:263-295) with height target
+ * 0.7 + 0.25 sin(w t + phase_e), w = 0.5*3.1415, t accumulated by 0.0005 per step and kept
+ * per env across calls.  phase_dev: DEVICE real [n] or NULL (0). */
+int Cassie2dBatchSquat(CassieBatch* h, int mode, int n_steps, const void* phase_dev,
+                       uint32_t* contact_mask_dev, void* stream);
+
+/* Host-buffer variants: same semantics, HOST pointers (pinned or pageable); the call copies
+ * host->device, launches, copies device->host and synchronises before returning. */
+int Cassie2dBatchStepHost(CassieBatch* h, int mode, const void* action_host, int n_substeps,
+                          void* state26_host /* out, may be NULL */);
+int Cassie2dBatchEnvStepHost(CassieBatch* h, int task, int mode, const void* action_host, int n_substeps,
+                             int flags, void* obs_host, void* reward_host, uint8_t* done_host);
+int Cassie2dBatchSquatHost(CassieBatch* h, int mode, int n_steps, const void* phase_host,
+                           void* state26_host /* out, may be NULL */);
+
+/* solver statistics of the last Step/EnvStep/Squat call, DEVICE int32 [n][4]:
+ * constraint rows, PGS sweeps, QP iterations, QP status of the last substep */
+int Cassie2dBatchGetStats(CassieBatch* h, int32_t* stats_dev, void* stream);
+int Cassie2dBatchSync(CassieBatch* h);
+
+/* Measures the non-tensor FP32 FMA throughput of the device (TFLOP/s) with a register-only
+ * FFMA kernel: the denominator of the step kernel's roofline (bench.py). */
+double CassieMeasureFp32Peak(int device);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+long long CassieKernelLaunchCount(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CASSIE2D_H_ */

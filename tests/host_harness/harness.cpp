@@ -1,0 +1,155 @@
+// TEST-ONLY: compiles the device engine (__host__ __device__ headers under
+// cassierl_b200/csrc) and the host flattener for the CPU, so that `-m "not gpu"` tests can
+// check the kernel's arithmetic against the oracle without a GPU.  Never loaded by the
+// product package.
+#include <cstring>
+#include <string>
+#include "../../cassierl_b200/csrc/mjcf_flatten.h"
+#include "../../cassierl_b200/csrc/cassie_step.cuh"
+
+using namespace cassie;
+
+static FlatModels g_models;
+static std::string g_err;
+
+template <typename T>
+static void run_steps(int n, double* q, double* qd, double* warm, const double* u, int* nrows, int* sweeps, unsigned* mask) {
+  PlanarModel<T> m = cast_model<T>(g_models.phys);
+  T tq[kNV], tv[kNV], tw[kNV], tu[kNU];
+  for (int i = 0; i < kNV; i++) { tq[i] = (T)q[i]; tv[i] = (T)qd[i]; tw[i] = (T)warm[i]; }
+  static thread_local Rows<T> rows;
+  for (int s = 0; s < n; s++) {
+    for (int i = 0; i < kNU; i++) tu[i] = (T)u[s * kNU + i];
+    StepStats st;
+    physics_step(m, tq, tv, tw, tu, rows, &st);
+    if (nrows) nrows[s] = st.nrows;
+    if (sweeps) sweeps[s] = st.sweeps;
+    if (mask) mask[s] = st.contact_mask;
+  }
+  for (int i = 0; i < kNV; i++) { q[i] = tq[i]; qd[i] = tv[i]; warm[i] = tw[i]; }
+}
+
+template <typename T>
+static void ctrl_step(int mode, int n, double* q, double* qd, double* warm, const double* act, int adim,
+                      double* u_out, double* op_out, double* traj_out, unsigned* mask_out, int* qp_out) {
+  PlanarModel<T> mp = cast_model<T>(g_models.phys), mc = cast_model<T>(g_models.ctrl);
+  T tq[kNV], tv[kNV], tw[kNV];
+  for (int i = 0; i < kNV; i++) { tq[i] = (T)q[i]; tv[i] = (T)qd[i]; tw[i] = (T)warm[i]; }
+  static thread_local Rows<T> rows;
+  for (int s = 0; s < n; s++) {
+    T a[8], u[kNU];
+    for (int i = 0; i < adim; i++) a[i] = (T)act[s * adim + i];
+    OpState<T> op;
+    StepStats st;
+    OscStats qs = {0, 0};
+    controller_step_dyn(mp, mc, mode, tq, tv, tw, a, rows, u, &op, &st, &qs);
+    if (u_out) for (int i = 0; i < kNU; i++) u_out[s * kNU + i] = u[i];
+    if (op_out) {
+      T o[18];
+      op_state_array(op, tq, tv, o);
+      for (int i = 0; i < 18; i++) op_out[s * 18 + i] = o[i];
+    }
+    if (traj_out) for (int i = 0; i < kNV; i++) { traj_out[s * 26 + i] = tq[i]; traj_out[s * 26 + 13 + i] = tv[i]; }
+    if (mask_out) mask_out[s] = st.contact_mask;
+    if (qp_out) { qp_out[2 * s] = qs.iters; qp_out[2 * s + 1] = qs.status; }
+  }
+  for (int i = 0; i < kNV; i++) { q[i] = tq[i]; qd[i] = tv[i]; warm[i] = tw[i]; }
+}
+
+// the squatting.py loop (squatting.py:8-16): mode 2 = standing_controller_jacobian, 3 = _osc
+template <typename T>
+static void squat(int mode, int n, double phase, double* q, double* qd, double* warm, double* traj_out, double* u_out) {
+  PlanarModel<T> mp = cast_model<T>(g_models.phys), mc = cast_model<T>(g_models.ctrl);
+  T tq[kNV], tv[kNV], tw[kNV];
+  for (int i = 0; i < kNV; i++) { tq[i] = (T)q[i]; tv[i] = (T)qd[i]; tw[i] = (T)warm[i]; }
+  static thread_local Rows<T> rows;
+  OpState<T> op;
+  {
+    Kin<T> kc;
+    forward_kinematics(mc, tq, tv, kc);
+    op_state_from_kin(mc, kc, tq, op);
+  }
+  const double w = 0.5 * 3.1415;
+  double t = 0.0;
+  for (int s = 0; s < n; s++) {
+    T o[18], a[8], u[kNU];
+    op_state_array(op, tq, tv, o);
+    const T zt = (T)(0.7 + 0.25 * sin(w * t + phase)), zdt = (T)(0.25 * cos(w * t + phase));
+    if (mode == kModeJacobian) squat_jacobian_action(o, zt, zdt, a);
+    else squat_osc_action(o, zt, zdt, a);
+    controller_step_dyn(mp, mc, mode, tq, tv, tw, a, rows, u, &op, (StepStats*)nullptr);
+    t = t + 0.0005;
+    if (traj_out) for (int i = 0; i < kNV; i++) { traj_out[s * 26 + i] = tq[i]; traj_out[s * 26 + 13 + i] = tv[i]; }
+    if (u_out) for (int i = 0; i < kNU; i++) u_out[s * kNU + i] = u[i];
+  }
+  for (int i = 0; i < kNV; i++) { q[i] = tq[i]; qd[i] = tv[i]; warm[i] = tw[i]; }
+}
+
+extern "C" {
+
+int hh_load(const char* path) { return flatten_mjcf_file(path, &g_models, &g_err) ? 0 : -1; }
+const char* hh_error() { return g_err.c_str(); }
+const void* hh_model(int ctrl) { return ctrl ? &g_models.ctrl : &g_models.phys; }
+int hh_model_size() { return (int)sizeof(PlanarModel<double>); }
+double hh_total_mass() { return g_models.phys.total_mass; }
+
+// u: [n][6] torques per step
+void hh_steps_f64(int n, double* q, double* qd, double* warm, const double* u, int* nrows, int* sweeps, unsigned* mask) {
+  run_steps<double>(n, q, qd, warm, u, nrows, sweeps, mask);
+}
+void hh_steps_f32(int n, double* q, double* qd, double* warm, const double* u, int* nrows, int* sweeps, unsigned* mask) {
+  run_steps<float>(n, q, qd, warm, u, nrows, sweeps, mask);
+}
+
+// dynamics pieces at (q, qd) on the physics (ctrl=0) or controller (ctrl=1) model
+void hh_dynamics(int ctrl, const double* q, const double* qd, double* M /*13x13 full*/, double* bias) {
+  const PlanarModel<double>& m = ctrl ? g_models.ctrl : g_models.phys;
+  Kin<double> k;
+  forward_kinematics(m, q, qd, k);
+  double Mm[kNV][kNV];
+  std::memset(Mm, 0, sizeof(Mm));
+  mass_matrix(m, k, Mm);
+  for (int i = 0; i < kNV; i++)
+    for (int j = 0; j <= i; j++) { M[i * kNV + j] = Mm[i][j]; M[j * kNV + i] = Mm[i][j]; }
+  bias_forces(m, k, bias);
+}
+
+// controller-model pieces (DynamicState.cpp:45-91): Jeq rows (4x13: Lx Lz Rx Rz), JeqdotQdot is
+// folded into gamma; returns bias (C+G+Dqd), gamma, and Nc applied to the identity (13x13)
+void hh_ctrl_dynamics(const double* q, const double* qd, double* bias, double* Jeq, double* gamma, double* Nc) {
+  const PlanarModel<double>& m = g_models.ctrl;
+  Kin<double> k;
+  forward_kinematics(m, q, qd, k);
+  static CtrlDyn<double> d;
+  ctrl_dynamics(m, k, qd, d);
+  for (int i = 0; i < kNV; i++) { bias[i] = d.bias[i]; gamma[i] = d.gamma[i]; }
+  for (int r = 0; r < 4; r++) {
+    double e[kNV];
+    expand_row(d.Jeq[r], r / 2, e);
+    for (int i = 0; i < kNV; i++) Jeq[r * kNV + i] = e[i];
+  }
+  for (int c = 0; c < kNV; c++) {
+    double x[kNV] = {0};
+    x[c] = 1;
+    apply_Nc(d, x);
+    for (int i = 0; i < kNV; i++) Nc[i * kNV + c] = x[i];
+  }
+}
+
+// mode: 0 torque 1 pd 2 jacobian 3 osc ; act [n][adim]; u_out [n][6]; op_out [n][18] = the
+// GetOperationalSpaceState a caller would read AFTER each step; traj_out [n][26] qpos,qvel
+void hh_ctrl_steps_f64(int mode, int n, double* q, double* qd, double* warm, const double* act, int adim,
+                       double* u_out, double* op_out, double* traj_out, unsigned* mask_out, int* qp_out) {
+  ctrl_step<double>(mode, n, q, qd, warm, act, adim, u_out, op_out, traj_out, mask_out, qp_out);
+}
+void hh_ctrl_steps_f32(int mode, int n, double* q, double* qd, double* warm, const double* act, int adim,
+                       double* u_out, double* op_out, double* traj_out, unsigned* mask_out, int* qp_out) {
+  ctrl_step<float>(mode, n, q, qd, warm, act, adim, u_out, op_out, traj_out, mask_out, qp_out);
+}
+void hh_squat_f64(int mode, int n, double phase, double* q, double* qd, double* warm, double* traj_out, double* u_out) {
+  squat<double>(mode, n, phase, q, qd, warm, traj_out, u_out);
+}
+void hh_squat_f32(int mode, int n, double phase, double* q, double* qd, double* warm, double* traj_out, double* u_out) {
+  squat<float>(mode, n, phase, q, qd, warm, traj_out, u_out);
+}
+}

