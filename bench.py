@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Headline benchmark: env-steps/s of the batched cassie2d_stiff step path (BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, libcassie2d.so)
+  python bench.py --impl reference --gpus N ...            # the CPU restatement on the host cores
+
+A "step" is one launch of the fused step kernel: `--substeps` (default 10, the Python envs' n,
+cassie2d.py:97) simulator steps of dt = 0.5 ms for every env of the batch, with the controller of
+the workload in the loop.  env-step = one simulator step of one env = one legacy Step* call
+(SURVEY 8d).  Weak scaling: every rank owns `--envs` envs (default 16384, BASELINE configs[2]);
+envs are independent, so there is no collective on the data path -- NCCL only reduces the rollout
+statistics after the timed region.
+
+Timing: per-step CUDA events on the launching stream, L2 flushed between timed steps, barrier +
+synchronize on both sides, MAX over ranks.  The JSON line carries `roofline` (FP32 pipe, measured
+peak), `cpu_baseline` (oracle port on the host cores, bounded sample), `e2e` (host buffers through
+the C-ABI *Host entry points, copies inside the timed region), `clocks`, `gpu_launches`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# Algorithmic FLOPs of ONE simulator step of ONE env (add+sub+mul+div+sqrt, FMA = 2), counted by
+# instantiating the engine on an operation-counting scalar (tools/count_flops.py).
+# Mean over the first 100 steps of the squatting stream with phases 2*pi*e/N, PGS at its 50 sweeps.
+FLOPS_PER_STEP = {"squat_osc": None, "squat_jacobian": 43.6e3, "torque_random": 19.4e3, "pd_env": 19.5e3}
+# Algorithmic HBM bytes of one launch per env: qpos, qvel, warm start read + written (13 reals each),
+# lagged op-space state 12 r/w, clock 8 r/w, stats 16 w, + per-workload action/phase/obs traffic.
+STATE_BYTES_PER_ENV_F32 = 2 * (39 * 4 + 12 * 4 + 8) + 16
+
+WORKLOADS = {
+    "squat_jacobian": "cassie2d_stiff.xml, squatting.py loop with standing_controller_jacobian (StepJacobian) in the kernel",
+    "squat_osc": "cassie2d_stiff.xml, squatting loop with standing_controller_osc + OSC_RBDL QP (StepOsc) in the kernel",
+    "torque_random": "cassie2d_stiff.xml, uniform-random torques held 10 steps (StepTorque)",
+    "pd_env": "cassie2d_stiff.xml, cassie_stand2d env step (StepPd x10 + obs/reward/done + auto-reset)",
+}
+DEFAULT_WORKLOAD = "squat_jacobian"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=50)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="native", choices=["native", "reference"])
+    p.add_argument("--envs", type=int, default=16384, help="envs per GPU")
+    p.add_argument("--substeps", type=int, default=10)
+    p.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    p.add_argument("--precision", type=int, default=32, choices=[32, 64])
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=10.0)
+    return p.parse_args()
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle)
+def oracle_rate(workload, n_envs, n_steps, threads, seed=1):
+    """env-steps/s of the fp64 CPU restatement (oracle/, OpenMP over envs) on this box."""
+    from oracle import oracle as O
+    O.build()
+    m = oracle_rate.model = getattr(oracle_rate, "model", None) or O.Model()
+    phase = 2 * np.pi * np.arange(n_envs) / max(n_envs, 1)
+    t0 = time.perf_counter()
+    if workload == "squat_jacobian":
+        n, _ = O.rollout(m, n_envs, n_steps, 2, phase=phase, n_threads=threads)
+    elif workload == "squat_osc":
+        n, _ = O.rollout(m, n_envs, n_steps, 3, phase=phase, n_threads=threads)
+    else:
+        rng = np.random.default_rng(seed)
+        hi = np.array([12.0, 12.0, 0.9, 12.0, 12.0, 0.9])
+        nact = (n_steps + 9) // 10
+        if workload == "torque_random":
+            a = rng.uniform(-1, 1, (n_envs, nact, 6)) * hi
+            n, _ = O.rollout(m, n_envs, n_steps, 0, actions=a, hold=10, n_threads=threads)
+        else:
+            lo = np.radians([-50.0, -164.0, -140.0, -50.0, -164.0, -140.0]); hh = np.radians([80.0, -37.0, -30.0, 80.0, -37.0, -30.0])
+            a = rng.uniform(lo, hh, (n_envs, nact, 6))
+            n, _ = O.rollout(m, n_envs, n_steps, 1, actions=a, hold=10, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return n / dt, dt
+
+
+def cpu_baseline(workload, seconds):
+    cores = os.cpu_count() or 1
+    rate, _ = oracle_rate(workload, cores, 50, cores)            # calibration
+    n_envs = cores * 4
+    n_steps = int(max(50, min(20000, rate * seconds / n_envs)))
+    rate, dt = oracle_rate(workload, n_envs, n_steps, cores)
+    return {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
+            "sample": "%d envs x %d sim steps of the same workload, fp64 oracle (oracle/, gcc -O3 -fopenmp), %.1f s" % (n_envs, n_steps, dt)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path cannot be built here (MuJoCo
+    1.50 / RBDL / qpOASES absent), so this times the oracle port on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_envs = 1024                                # bounded sample of the 16384-env workload
+    for _ in range(args.warmup):
+        oracle_rate(args.workload, n_envs, args.substeps, cores)
+    t0 = time.perf_counter()
+    total = 0
+    for _ in range(args.steps):
+        r, dt = oracle_rate(args.workload, n_envs, args.substeps, cores)
+        total += n_envs * args.substeps
+    el = time.perf_counter() - t0
+    v = total / el
+    line = {"impl": "reference", "metric": "env-steps/sec cassie2d_stiff", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload], "envs_per_step_sample": n_envs, "substeps": args.substeps,
+                       "note": "CPU restatement (oracle port) of MuJoCo+RBDL path; the reference itself is unbuildable here"},
+            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                             "sample": "%d envs x %d sim steps per step, %d steps" % (n_envs, args.substeps, args.steps)},
+            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- native arm
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from cassierl_b200 import envs, lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the native arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = lib.load()
+    n, sub, wl = args.envs, args.substeps, args.workload
+    dt_t = torch.float64 if args.precision == 64 else torch.float32
+    rs = 8 if args.precision == 64 else 4
+    gid0 = rank * n                                   # global env ids: results independent of the GPU count
+    phase = (2 * np.pi * (gid0 + np.arange(n)) / (n * world)).astype(np.float64)
+    gen = np.random.default_rng(1 + rank)
+    hi = np.array([12.0, 12.0, 0.9, 12.0, 12.0, 0.9])
+    total_steps = args.warmup + args.steps
+
+    def make():
+        if wl == "pd_env":
+            return envs.Cassie2dBatchEnv(n, device=local, task="stand", control_mode="PD", precision=args.precision)
+        return envs.Cassie2dBatch(n, device=local, precision=args.precision)
+
+    # ---- inputs resident in HBM before the timed region
+    obj = make()
+    b = obj.batch if wl == "pd_env" else obj
+    phase_d = torch.tensor(phase, dtype=dt_t, device=dev)
+    if wl == "torque_random":
+        acts = torch.tensor(gen.uniform(-1, 1, (total_steps, n, 6)) * hi, dtype=dt_t, device=dev)
+    elif wl == "pd_env":
+        lo, hh = obj.action_space
+        acts = torch.tensor(gen.uniform(lo, hh, (total_steps, n, 6)), dtype=dt_t, device=dev)
+        obj.reset()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def one_step(k):
+        if wl == "squat_jacobian":
+            b.squat(lib.MODE_JACOBIAN, sub, phase=phase_d)
+        elif wl == "squat_osc":
+            b.squat(lib.MODE_OSC, sub, phase=phase_d)
+        elif wl == "torque_random":
+            b.step_torque(acts[k], sub)
+        else:
+            obj.step(acts[k], n=sub)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        one_step(k)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = L.CassieKernelLaunchCount()
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()                                   # L2 flush, outside the timed events
+        ev[k][0].record()
+        one_step(args.warmup + k)
+        ev[k][1].record()
+    barrier()
+    launches = L.CassieKernelLaunchCount() - launches0
+    ms = sum(a.elapsed_time(c) for a, c in ev)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    # rollout statistics (NCCL reduce, outside the timed region): mean pelvis height, envs below 0.5 m
+    s = b.get_general_state()
+    stats = torch.stack([s[:, 1].double().sum(), (s[:, 1] < 0.5).double().sum(), (~torch.isfinite(s).all(dim=1)).double().sum()])
+    if world > 1:
+        dist.all_reduce(stats)
+    value = world * n * sub * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI entry points (pinned host memory in and out)
+    obj2 = make()
+    b2 = obj2.batch if wl == "pd_env" else obj2
+    if wl == "pd_env":
+        obj2.reset()
+    ph_h = torch.tensor(phase, dtype=dt_t).pin_memory()
+    st_h = torch.empty((n, 26), dtype=dt_t).pin_memory()
+    if wl in ("torque_random", "pd_env"):
+        acts_h = acts.cpu().pin_memory()
+        obs_h = torch.empty((n, 17), dtype=dt_t).pin_memory(); rew_h = torch.empty(n, dtype=dt_t).pin_memory()
+        done_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+
+    def one_e2e(k):
+        if wl == "squat_jacobian":
+            b2.squat_host(lib.MODE_JACOBIAN, sub, ph_h, st_h); return n * rs, n * 26 * rs
+        if wl == "squat_osc":
+            b2.squat_host(lib.MODE_OSC, sub, ph_h, st_h); return n * rs, n * 26 * rs
+        if wl == "torque_random":
+            b2.step_host(lib.MODE_TORQUE, acts_h[k], sub, st_h); return n * 6 * rs, n * 26 * rs
+        obj2.step_host(acts_h[k], obs_h, rew_h, done_h, n=sub); return n * 6 * rs, n * (17 * rs + rs + 1)
+
+    for k in range(args.warmup):
+        h2d, d2h = one_e2e(k)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        one_e2e(args.warmup + k)
+    torch.cuda.synchronize()
+    el = time.perf_counter() - t0
+    t = torch.tensor([el], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * sub * args.steps / float(t.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        fp32_peak = L.CassieMeasureFp32Peak(local)            # TFLOP/s, measured live on this GPU
+        fl = FLOPS_PER_STEP.get(wl) or 0.0
+        flops_launch = fl * n * sub
+        ms_launch = ms_max / args.steps
+        achieved = flops_launch / (ms_launch * 1e-3) / 1e12
+        bytes_launch = n * (STATE_BYTES_PER_ENV_F32 * rs // 4 + rs)
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        line = {
+            "metric": "env-steps/sec cassie2d_stiff @16k envs", "value": value, "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_launch, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic",
+            "config": {"workload": WORKLOADS[wl], "workload_key": wl, "envs_per_gpu": n, "sim_steps_per_launch": sub,
+                       "policy_steps_per_s": value / sub, "l2": "flushed between timed steps (256 MiB memset)",
+                       "parallelism": "env-sharded dp%d, no data-path collective" % world},
+            "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp32_peak if fp32_peak > 0 else None, "traffic": None,
+                         "peak_source": "measured live: register-only FFMA kernel (CassieMeasureFp32Peak); MEASURED_PEAKS.json has no FP32 figure",
+                         "flops_per_env_step": fl, "kernel_ms": ms_launch,
+                         "hbm": {"achieved_gbs": bytes_launch / (ms_launch * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                                 "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback",
+                                 "algorithmic_bytes_per_launch": bytes_launch}},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "stats": {"mean_pelvis_z": float(stats[0].item()) / (n * world), "envs_below_0.5m": int(stats[1].item()),
+                      "non_finite_envs": int(stats[2].item())},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(wl, args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

@@ -26,7 +26,7 @@ struct BatchView {
   T* op;            // [12][n]  lagged op-space state (RBDL state of the last Step*, App. D.1)
   double* clock;    // [n]      squatting.py's t  /  cassie2d.py's self.time (seconds, double)
   T* jsum0;         // [n]      frozen qstate joint sum of the imitation reward (App. D.4)
-  int32_t* stats;   // [4][n]   rows, PGS sweeps, QP iterations, QP status of the last substep
+  int32_t* stats;   // [n][4]   rows, PGS sweeps, QP iterations, QP status of the last substep
   const double* traj;  // [traj_rows][13] reference qpos (device), may be null
   int traj_rows;
   double traj_tmax;
@@ -62,6 +62,7 @@ struct Launch {
   static cudaError_t refresh_op(const ModelPair<T>& mp, const BatchView<T>& v, const uint8_t* mask, cudaStream_t s);
   static cudaError_t get_general(const BatchView<T>& v, T* state26, cudaStream_t s);
   static cudaError_t get_op(const BatchView<T>& v, T* state18, cudaStream_t s);
+  static cudaError_t warm_io(const BatchView<T>& v, T* buf, int write_to_env, cudaStream_t s);
   static cudaError_t env_reset(const ModelPair<T>& mp, const BatchView<T>& v, int task, int flags, const T* state26,
                                T* obs, cudaStream_t s);
 };

@@ -287,13 +287,20 @@ int Cassie2dBatchGetStats(CassieBatch* h, int32_t* stats_dev, void* stream) {
   if (!h || !stats_dev) return fail("null argument");
   if (set_device(h)) return -1;
   const int32_t* src = h->precision == 64 ? h->v64.stats : h->v32.stats;
-  // stored [4][n] -> returned [n][4]
-  std::vector<int32_t> tmp(4 * (size_t)h->n), out(4 * (size_t)h->n);
-  CU_OK(cudaStreamSynchronize((cudaStream_t)stream));
-  CU_OK(cudaMemcpy(tmp.data(), src, tmp.size() * 4, cudaMemcpyDeviceToHost));
-  for (int e = 0; e < h->n; e++)
-    for (int k = 0; k < 4; k++) out[(size_t)e * 4 + k] = tmp[(size_t)k * h->n + e];
-  CU_OK(cudaMemcpy(stats_dev, out.data(), out.size() * 4, cudaMemcpyHostToDevice));
+  CU_OK(cudaMemcpyAsync(stats_dev, src, sizeof(int32_t) * 4 * (size_t)h->n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int Cassie2dBatchSetWarmStart(CassieBatch* h, const void* qacc_dev, void* stream) {
+  if (!h || !qacc_dev) return fail("null argument");
+  if (set_device(h)) return -1;
+  DISPATCH(h, CU_OK(Launch<R>::warm_io(BV<R>(h), (R*)qacc_dev, 1, (cudaStream_t)stream)));
+  return 0;
+}
+int Cassie2dBatchGetWarmStart(CassieBatch* h, void* qacc_dev, void* stream) {
+  if (!h || !qacc_dev) return fail("null argument");
+  if (set_device(h)) return -1;
+  DISPATCH(h, CU_OK(Launch<R>::warm_io(BV<R>(h), (R*)qacc_dev, 0, (cudaStream_t)stream)));
   return 0;
 }
 

@@ -51,10 +51,8 @@ __device__ __forceinline__ void store_op(const BatchView<T>& v, int e, const OpS
   }
 }
 __device__ __forceinline__ void store_stats(int32_t* stats, int n, int e, const StepStats& st, const OscStats& qs) {
-  stats[e] = st.nrows;
-  stats[(size_t)n + e] = st.sweeps;
-  stats[(size_t)2 * n + e] = qs.iters;
-  stats[(size_t)3 * n + e] = qs.status;
+  (void)n;
+  reinterpret_cast<int4*>(stats)[e] = make_int4(st.nrows, st.sweeps, qs.iters, qs.status);
 }
 
 // StateGeneral memory order (RobotInterface.h:34-41, converters :98-128) <-> qpos/qvel
@@ -297,6 +295,19 @@ __global__ void __launch_bounds__(128) k_get_general(const BatchView<T> v, T* __
   }
 }
 
+// qacc_warmstart in/out, real [n][13] (checkpoint / teacher-forced parity tests)
+template <typename T>
+__global__ void __launch_bounds__(128) k_warm_io(const BatchView<T> v, T* __restrict__ buf, int write_to_env) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= v.n) return;
+  const int n = v.n;
+#pragma unroll
+  for (int i = 0; i < kNV; i++) {
+    if (write_to_env) v.warm[(size_t)i * n + e] = buf[(size_t)e * kNV + i];
+    else buf[(size_t)e * kNV + i] = v.warm[(size_t)i * n + e];
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(128) k_get_op(const BatchView<T> v, T* __restrict__ out) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -385,6 +396,12 @@ cudaError_t Launch<T>::get_general(const BatchView<T>& v, T* state26, cudaStream
 template <typename T>
 cudaError_t Launch<T>::get_op(const BatchView<T>& v, T* state18, cudaStream_t s) {
   k_get_op<T><<<grid_for(v.n, 128), 128, 0, s>>>(v, state18);
+  count_launch();
+  return cudaGetLastError();
+}
+template <typename T>
+cudaError_t Launch<T>::warm_io(const BatchView<T>& v, T* buf, int write_to_env, cudaStream_t s) {
+  k_warm_io<T><<<grid_for(v.n, 128), 128, 0, s>>>(v, buf, write_to_env);
   count_launch();
   return cudaGetLastError();
 }

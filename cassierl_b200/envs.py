@@ -113,6 +113,17 @@ class Cassie2dBatch:
                                                  contact_mask.data_ptr() if contact_mask is not None else None,
                                                  _stream_ptr()), "Squat")
 
+    def set_warm_start(self, qacc):
+        w = self._t(qacc, 13)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.Cassie2dBatchSetWarmStart(self.h, w.data_ptr(), _stream_ptr()), "SetWarmStart")
+
+    def get_warm_start(self):
+        out = self.empty(13)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.Cassie2dBatchGetWarmStart(self.h, out.data_ptr(), _stream_ptr()), "GetWarmStart")
+        return out
+
     def stats(self):
         out = torch.empty((self.n, 4), dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):

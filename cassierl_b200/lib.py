@@ -22,7 +22,7 @@ BATCH_SYMBOLS = ["CassieGetLastError", "Cassie2dBatchInit", "Cassie2dBatchDestro
                  "Cassie2dBatchSetState", "Cassie2dBatchGetGeneralState", "Cassie2dBatchGetOperationalSpaceState",
                  "Cassie2dBatchStep", "Cassie2dBatchEnvStep", "Cassie2dBatchEnvReset", "Cassie2dBatchSetTrajectory",
                  "Cassie2dBatchSquat", "Cassie2dBatchStepHost", "Cassie2dBatchEnvStepHost", "Cassie2dBatchSquatHost",
-                 "Cassie2dBatchGetStats", "Cassie2dBatchSync", "CassieMeasureFp32Peak", "CassieKernelLaunchCount"]
+                 "Cassie2dBatchGetStats", "Cassie2dBatchSetWarmStart", "Cassie2dBatchGetWarmStart", "Cassie2dBatchSync", "CassieMeasureFp32Peak", "CassieKernelLaunchCount"]
 
 _lib = None
 
@@ -57,6 +57,8 @@ def load():
     L.Cassie2dBatchEnvStepHost.argtypes = [vp, ci, ci, vp, ci, ci, vp, vp, vp]
     L.Cassie2dBatchSquatHost.argtypes = [vp, ci, ci, vp, vp]
     L.Cassie2dBatchGetStats.argtypes = [vp, vp, vp]
+    L.Cassie2dBatchSetWarmStart.argtypes = [vp, vp, vp]
+    L.Cassie2dBatchGetWarmStart.argtypes = [vp, vp, vp]
     L.CassieMeasureFp32Peak.restype = cd
     L.CassieMeasureFp32Peak.argtypes = [ci]
     L.CassieKernelLaunchCount.restype = ct.c_longlong

@@ -145,6 +145,10 @@ int Cassie2dBatchSquatHost(CassieBatch* h, int mode, int n_steps, const void* ph
 /* solver statistics of the last Step/EnvStep/Squat call, DEVICE int32 [n][4]:
  * constraint rows, PGS sweeps, QP iterations, QP status of the last substep */
 int Cassie2dBatchGetStats(CassieBatch* h, int32_t* stats_dev, void* stream);
+/* solver warm start (mjData.qacc_warmstart, carried across steps and resets): DEVICE real [n][13].
+ * Together with the general state this is the complete per-env simulator state. */
+int Cassie2dBatchSetWarmStart(CassieBatch* h, const void* qacc_dev, void* stream);
+int Cassie2dBatchGetWarmStart(CassieBatch* h, void* qacc_dev, void* stream);
 int Cassie2dBatchSync(CassieBatch* h);
 
 /* Measures the non-tensor FP32 FMA throughput of the device (TFLOP/s) with a register-only

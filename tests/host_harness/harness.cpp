@@ -9,6 +9,41 @@
 
 using namespace cassie;
 
+// ---- operation-counting scalar: the engine instantiated on it yields the exact algorithmic
+// FLOP count of one step (bench.py's roofline numerator)
+struct OpCount { long add = 0, mul = 0, div = 0, sqrt_ = 0, trig = 0, cmp = 0; };
+static thread_local OpCount g_ops;
+struct CountD {
+  double v;
+  CountD() : v(0) {}
+  CountD(double x) : v(x) {}
+  CountD(float x) : v(x) {}
+  CountD(int x) : v(x) {}
+  explicit operator double() const { return v; }
+};
+static inline CountD operator+(CountD a, CountD b) { g_ops.add++; return CountD(a.v + b.v); }
+static inline CountD operator-(CountD a, CountD b) { g_ops.add++; return CountD(a.v - b.v); }
+static inline CountD operator*(CountD a, CountD b) { g_ops.mul++; return CountD(a.v * b.v); }
+static inline CountD operator/(CountD a, CountD b) { g_ops.div++; return CountD(a.v / b.v); }
+static inline CountD operator-(CountD a) { return CountD(-a.v); }
+static inline CountD& operator+=(CountD& a, CountD b) { g_ops.add++; a.v += b.v; return a; }
+static inline CountD& operator-=(CountD& a, CountD b) { g_ops.add++; a.v -= b.v; return a; }
+static inline CountD& operator*=(CountD& a, CountD b) { g_ops.mul++; a.v *= b.v; return a; }
+static inline bool operator<(CountD a, CountD b) { g_ops.cmp++; return a.v < b.v; }
+static inline bool operator>(CountD a, CountD b) { g_ops.cmp++; return a.v > b.v; }
+static inline bool operator<=(CountD a, CountD b) { g_ops.cmp++; return a.v <= b.v; }
+static inline bool operator>=(CountD a, CountD b) { g_ops.cmp++; return a.v >= b.v; }
+static inline bool operator==(CountD a, CountD b) { g_ops.cmp++; return a.v == b.v; }
+namespace cassie {
+template <> struct Num<CountD> {
+  static void sincos_(CountD a, CountD* s, CountD* c) { g_ops.trig++; s->v = sin(a.v); c->v = cos(a.v); }
+  static CountD sqrt_(CountD a) { g_ops.sqrt_++; return CountD(sqrt(a.v)); }
+  static CountD abs_(CountD a) { return CountD(fabs(a.v)); }
+  static CountD pow_(CountD a, CountD b) { g_ops.trig++; return CountD(pow(a.v, b.v)); }
+  static CountD exp_(CountD a) { g_ops.trig++; return CountD(exp(a.v)); }
+};
+}  // namespace cassie
+
 static FlatModels g_models;
 static std::string g_err;
 
@@ -85,7 +120,27 @@ static void squat(int mode, int n, double phase, double* q, double* qd, double* 
   for (int i = 0; i < kNV; i++) { q[i] = tq[i]; qd[i] = tv[i]; warm[i] = tw[i]; }
 }
 
+static_assert(sizeof(PlanarModel<CountD>) == sizeof(PlanarModel<double>), "CountD must wrap exactly one double");
+
 extern "C" {
+
+// exact operation counts of ONE Step* call at the given state: out[0..5] = add/sub, mul, div, sqrt,
+// transcendental (sincos/pow/exp), compare ; out[6] = constraint rows, out[7] = PGS sweeps
+void hh_count_ops(int mode, const double* q, const double* qd, const double* warm, const double* act, int adim, long* out) {
+  PlanarModel<CountD> mp, mc;
+  std::memcpy((void*)&mp, &g_models.phys, sizeof(mp));
+  std::memcpy((void*)&mc, &g_models.ctrl, sizeof(mc));
+  CountD tq[kNV], tv[kNV], tw[kNV], a[8], u[kNU];
+  for (int i = 0; i < kNV; i++) { tq[i].v = q[i]; tv[i].v = qd[i]; tw[i].v = warm[i]; }
+  for (int i = 0; i < adim; i++) a[i].v = act[i];
+  static thread_local Rows<CountD> rows;
+  OpState<CountD> op;
+  StepStats st;
+  g_ops = OpCount();
+  controller_step_dyn(mp, mc, mode, tq, tv, tw, a, rows, u, &op, &st);
+  out[0] = g_ops.add; out[1] = g_ops.mul; out[2] = g_ops.div; out[3] = g_ops.sqrt_; out[4] = g_ops.trig; out[5] = g_ops.cmp;
+  out[6] = st.nrows; out[7] = st.sweeps;
+}
 
 int hh_load(const char* path) { return flatten_mjcf_file(path, &g_models, &g_err) ? 0 : -1; }
 const char* hh_error() { return g_err.c_str(); }
