@@ -32,8 +32,10 @@ if ROOT not in sys.path:
 
 # Algorithmic FLOPs of ONE simulator step of ONE env (add+sub+mul+div+sqrt, FMA = 2), counted by
 # instantiating the engine on an operation-counting scalar (tools/count_flops.py).
-# Mean over the first 100 steps of the squatting stream with phases 2*pi*e/N, PGS at its 50 sweeps.
-FLOPS_PER_STEP = {"squat_osc": None, "squat_jacobian": 43.6e3, "torque_random": 19.4e3, "pd_env": 19.5e3}
+# Mean over the first 100 steps of the squatting stream at four phases (9.5-11 constraint rows, PGS at
+# its 50-sweep cap); the fast path's inert padding rows are NOT counted.  torque_random / pd_env use
+# the torque / PD step figures of the same stream (their own streams visit more contact states).
+FLOPS_PER_STEP = {"squat_osc": 48.7e3, "squat_jacobian": 47.6e3, "torque_random": 24.2e3, "pd_env": 22.6e3}
 # Algorithmic HBM bytes of one launch per env: qpos, qvel, warm start read + written (13 reals each),
 # lagged op-space state 12 r/w, clock 8 r/w, stats 16 w, + per-workload action/phase/obs traffic.
 STATE_BYTES_PER_ENV_F32 = 2 * (39 * 4 + 12 * 4 + 8) + 16
@@ -44,7 +46,7 @@ WORKLOADS = {
     "torque_random": "cassie2d_stiff.xml, uniform-random torques held 10 steps (StepTorque)",
     "pd_env": "cassie2d_stiff.xml, cassie_stand2d env step (StepPd x10 + obs/reward/done + auto-reset)",
 }
-DEFAULT_WORKLOAD = "squat_jacobian"
+DEFAULT_WORKLOAD = "squat_osc"   # BASELINE.json configs[2]: 16384 envs, OSC_RBDL squatting controller in the loop
 
 
 def parse():

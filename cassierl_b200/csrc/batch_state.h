@@ -13,6 +13,8 @@ template <typename T>
 struct ModelPair {
   PlanarModel<T> phys;  // MuJoCo's view of the MJCF (mj_loadXML, Cassie2d.cpp:48)
   PlanarModel<T> ctrl;  // the RBDL loader's view (DynamicModel::LoadModel, Cassie2d.cpp:43)
+  PlanarModel<double> phys_d;  // phys in double: the position pass of every step runs in double (planar_engine.cuh)
+  PlanarModel<double> ctrl_d;  // the same in double: the OSC controller always runs in double (osc_qp.cuh)
 };
 
 // All arrays are [field][env] (env fastest) so that a warp's 32 envs read one 128-byte line
@@ -26,6 +28,8 @@ struct BatchView {
   T* op;            // [12][n]  lagged op-space state (RBDL state of the last Step*, App. D.1)
   double* clock;    // [n]      squatting.py's t  /  cassie2d.py's self.time (seconds, double)
   T* jsum0;         // [n]      frozen qstate joint sum of the imitation reward (App. D.4)
+  uint32_t* qp_set; // [n]      OSC QP partition (free / at-lower / at-upper) carried across steps, like
+                    //          the qpOASES hot start that survives resets in the reference (App. D.3)
   int32_t* stats;   // [n][4]   rows, PGS sweeps, QP iterations, QP status of the last substep
   const double* traj;  // [traj_rows][13] reference qpos (device), may be null
   int traj_rows;

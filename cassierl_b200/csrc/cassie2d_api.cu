@@ -92,6 +92,7 @@ static int alloc_view(CassieBatch* h, BatchView<T>& v) {
   CU_OK(A((void**)&v.clock, sizeof(double) * n));
   CU_OK(A((void**)&v.jsum0, sizeof(T) * n));
   CU_OK(A((void**)&v.stats, sizeof(int32_t) * 4 * n));
+  CU_OK(A((void**)&v.qp_set, sizeof(uint32_t) * n));
   v.traj = nullptr; v.traj_rows = 0; v.traj_tmax = 1.0;
   CU_OK(A(&h->scratch_state, sizeof(T) * 26));
   CU_OK(A(&h->d_action, sizeof(T) * 7 * n));
@@ -160,6 +161,10 @@ CassieBatch* Cassie2dBatchInit(int n_envs, int device, const char* xml_path, int
   h->mp32.ctrl = cast_model<float>(h->models.ctrl);
   h->mp64.phys = h->models.phys;
   h->mp64.ctrl = h->models.ctrl;
+  h->mp32.phys_d = h->models.phys;
+  h->mp64.phys_d = h->models.phys;
+  h->mp32.ctrl_d = h->models.ctrl;
+  h->mp64.ctrl_d = h->models.ctrl;
   if (cudaSetDevice(device) != cudaSuccess) { fail("cudaSetDevice failed"); delete h; return nullptr; }
   int rc = precision == 64 ? alloc_view<double>(h, h->v64) : alloc_view<float>(h, h->v32);
   if (rc == 0 && cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) rc = fail("stream create failed");

@@ -16,33 +16,58 @@ CASSIE_HD constexpr int action_dim(int mode) { return mode == kModeOsc ? 7 : 6; 
 // `op` (may be null) receives the operational-space quantities of the state at the START of
 // this step -- what GetOperationalSpaceState reports after the step.
 // MODE is a template parameter so that each control mode gets its own register allocation.
-template <int MODE, typename T>
-CASSIE_HD void controller_step(const PlanarModel<T>& mp, const PlanarModel<T>& mc, T q[kNV], T qd[kNV],
+// The controller model may be held in a wider type TC than the physics (T): the fp32 build runs
+// the OSC controller in double (its QP is ill-conditioned, osc_qp.cuh), everything else in T.
+// mg = the physics model in the type of the position pass (planar_engine.cuh physics_step).
+template <int MODE, typename T, typename TG, typename TC>
+CASSIE_HD void controller_step(const PlanarModel<T>& mp, const PlanarModel<TG>& mg, const PlanarModel<TC>& mc, T q[kNV], T qd[kNV],
                                T warm[kNV], const T* act, Rows<T>& rows, T u[kNU], OpState<T>* op,
-                               StepStats* st, OscStats* qst = nullptr) {
+                               StepStats* st, OscStats* qst = nullptr, unsigned* qp_set = nullptr) {
   if (MODE == kModeTorque) {
     CASSIE_UNROLL
     for (int i = 0; i < kNU; i++) u[i] = act[i];
   } else if (MODE == kModePd) {
-    pd_control(mc, q, qd, act, u);
+    CASSIE_UNROLL
+    for (int a = 0; a < kNU; a++) {  // Cassie2d.cpp:96-112: gains are in ctrl units
+      T qj = T(0), vj = T(0);
+      CASSIE_UNROLL
+      for (int i = 3; i < kNV; i++)
+        if (mp.act_dof[a] == i) { qj = q[i]; vj = qd[i]; }
+      u[a] = T(10) * (act[a] - qj) + T(5) * (T(0) - vj);
+    }
   }
   if (op || MODE >= kModeJacobian) {
-    Kin<T> kc;
-    forward_kinematics(mc, q, qd, kc);
-    if (op) op_state_from_kin(mc, kc, q, *op);
-    if (MODE == kModeJacobian) jacobian_control(mc, kc, qd, act, u);
-    else if (MODE == kModeOsc) osc_control(mc, kc, qd, act, u, qst);
+    TC qc[kNV], qdc[kNV];
+    CASSIE_UNROLL
+    for (int i = 0; i < kNV; i++) { qc[i] = (TC)q[i]; qdc[i] = (TC)qd[i]; }
+    Kin<TC> kc;
+    forward_kinematics(mc, qc, qdc, kc);
+    if (op) {
+      OpState<TC> oc;
+      op_state_from_kin(mc, kc, qc, oc);
+      CASSIE_UNROLL
+      for (int i = 0; i < 4; i++) { op->body[i] = (T)oc.body[i]; op->left[i] = (T)oc.left[i]; op->right[i] = (T)oc.right[i]; }
+    }
+    if (MODE >= kModeJacobian) {
+      TC ac[7], uc[kNU];
+      CASSIE_UNROLL
+      for (int i = 0; i < action_dim(MODE); i++) ac[i] = (TC)act[i];
+      if (MODE == kModeJacobian) jacobian_control(mc, kc, qdc, ac, uc);
+      else osc_control(mc, kc, qdc, ac, uc, qst, qp_set);
+      CASSIE_UNROLL
+      for (int i = 0; i < kNU; i++) u[i] = (T)uc[i];
+    }
   }
-  physics_step(mp, q, qd, warm, u, rows, st);
+  physics_step(mp, mg, q, qd, warm, u, rows, st);
 }
-template <typename T>
-CASSIE_HD void controller_step_dyn(const PlanarModel<T>& mp, const PlanarModel<T>& mc, int mode, T q[kNV], T qd[kNV],
+template <typename T, typename TG, typename TC>
+CASSIE_HD void controller_step_dyn(const PlanarModel<T>& mp, const PlanarModel<TG>& mg, const PlanarModel<TC>& mc, int mode, T q[kNV], T qd[kNV],
                                    T warm[kNV], const T* act, Rows<T>& rows, T u[kNU], OpState<T>* op,
-                                   StepStats* st, OscStats* qst = nullptr) {
-  if (mode == kModeTorque) controller_step<kModeTorque>(mp, mc, q, qd, warm, act, rows, u, op, st, qst);
-  else if (mode == kModePd) controller_step<kModePd>(mp, mc, q, qd, warm, act, rows, u, op, st, qst);
-  else if (mode == kModeJacobian) controller_step<kModeJacobian>(mp, mc, q, qd, warm, act, rows, u, op, st, qst);
-  else controller_step<kModeOsc>(mp, mc, q, qd, warm, act, rows, u, op, st, qst);
+                                   StepStats* st, OscStats* qst = nullptr, unsigned* qp_set = nullptr) {
+  if (mode == kModeTorque) controller_step<kModeTorque>(mp, mg, mc, q, qd, warm, act, rows, u, op, st, qst, qp_set);
+  else if (mode == kModePd) controller_step<kModePd>(mp, mg, mc, q, qd, warm, act, rows, u, op, st, qst, qp_set);
+  else if (mode == kModeJacobian) controller_step<kModeJacobian>(mp, mg, mc, q, qd, warm, act, rows, u, op, st, qst, qp_set);
+  else controller_step<kModeOsc>(mp, mg, mc, q, qd, warm, act, rows, u, op, st, qst, qp_set);
 }
 
 // standing_controller_jacobian (cassie2d.py:297-331): s = GetOperationalSpaceState array

@@ -94,12 +94,12 @@ CASSIE_HD void pivot_accelerations(const Kin<T>& k, PivotAcc<T>& pa) {
     CASSIE_UNROLL
     for (int a = 0; a < kLegLinks; a++) {
       const int p = link_parent(a);
-      T apx, apz, wp, ppx, ppz;
-      if (p < 0) { apx = T(0); apz = T(0); wp = k.w0; ppx = T(0); ppz = T(0); }
-      else { apx = pa.ax[L][p]; apz = pa.az[L][p]; wp = k.w[L][p]; ppx = k.px[L][p]; ppz = k.pz[L][p]; }
+      T apx, apz, wp;
+      if (p < 0) { apx = T(0); apz = T(0); wp = k.w0; }
+      else { apx = pa.ax[L][p]; apz = pa.az[L][p]; wp = k.w[L][p]; }
       const T w2 = wp * wp;
-      pa.ax[L][a] = apx - w2 * (k.px[L][a] - ppx);
-      pa.az[L][a] = apz - w2 * (k.pz[L][a] - ppz);
+      pa.ax[L][a] = apx - w2 * k.dx[L][a];
+      pa.az[L][a] = apz - w2 * k.dz[L][a];
     }
   }
 }
@@ -285,8 +285,8 @@ CASSIE_HD void ctrl_dynamics(const PlanarModel<T>& m, const Kin<T>& k, const T* 
     rot(k.c[L][kRod], k.s[L][kRod], m.eq_a1[L][0], m.eq_a1[L][1], ax, az);
     rot(k.c[L][kTarsus], k.s[L][kTarsus], m.eq_a2[L][0], m.eq_a2[L][1], bx, bz);
     T J1x[8], J1z[8], J2x[8], J2z[8];
-    point_jac(m, k, L, kRod, k.px[L][kRod] + ax, k.pz[L][kRod] + az, J1x, J1z);
-    point_jac(m, k, L, kTarsus, k.px[L][kTarsus] + bx, k.pz[L][kTarsus] + bz, J2x, J2z);
+    point_jac(m, k, L, kRod, ax, az, J1x, J1z);
+    point_jac(m, k, L, kTarsus, bx, bz, J2x, J2z);
     CASSIE_UNROLL
     for (int c = 0; c < 8; c++) { d.Jeq[2 * L][c] = J1x[c] - J2x[c]; d.Jeq[2 * L + 1][c] = J1z[c] - J2z[c]; }
     const T w1 = k.w[L][kRod] * k.w[L][kRod], w2 = k.w[L][kTarsus] * k.w[L][kTarsus];
@@ -358,7 +358,7 @@ CASSIE_HD void jacobian_control(const PlanarModel<T>& m, const Kin<T>& k, const 
     const int s0 = 2 + 2 * L, s1 = 3 + 2 * L;
     rot(k.c[L][kToe], k.s[L][kToe], T(0.5) * (m.site_off[s0][0] + m.site_off[s1][0]),
         T(0.5) * (m.site_off[s0][1] + m.site_off[s1][1]), rx, rz);
-    point_jac(m, k, L, kToe, k.px[L][kToe] + rx, k.pz[L][kToe] + rz, Jx, Jz);
+    point_jac(m, k, L, kToe, rx, rz, Jx, Jz);
     Jr[0] = T(0); Jr[1] = T(0); Jr[2] = T(1);
     CASSIE_UNROLL
     for (int b = 0; b < kLegLinks; b++) Jr[3 + b] = link_anc(kToe, b) ? m.sgn[L][b] : T(0);

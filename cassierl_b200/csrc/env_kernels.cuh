@@ -8,7 +8,14 @@
 
 namespace cassie {
 
-constexpr int kBlock = 32;  // one warp per CTA: 16384 envs -> 512 CTAs spread over 148 SMs x 4 SMSPs
+constexpr int kBlock = 32;
+
+// controller model of a mode: OSC runs in double in every build, the other modes in T
+template <int MODE, typename T>
+__device__ __forceinline__ const auto& ctrl_model(const ModelPair<T>& mp) {
+  if constexpr (MODE == kModeOsc) return mp.ctrl_d;
+  else return mp.ctrl;
+}  // one warp per CTA: 16384 envs -> 512 CTAs spread over 148 SMs x 4 SMSPs
 
 template <typename T>
 __device__ __forceinline__ void load_env(const BatchView<T>& v, int e, T q[kNV], T qd[kNV], T w[kNV]) {
@@ -80,8 +87,10 @@ __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ ModelPa
   OpState<T> op;
   StepStats st = {0, 0, 0u};
   OscStats qs = {0, 0};
+  unsigned qps = v.qp_set[e];
   for (int s = 0; s < n_sub; s++)
-    controller_step<MODE>(mp.phys, mp.ctrl, q, qd, w, act, rows, u, s == n_sub - 1 ? &op : nullptr, &st, &qs);
+    controller_step<MODE>(mp.phys, mp.phys_d, ctrl_model<MODE>(mp), q, qd, w, act, rows, u, s == n_sub - 1 ? &op : nullptr, &st, &qs, &qps);
+  v.qp_set[e] = qps;
   store_env(v, e, q, qd, w);
   if (n_sub > 0) {
     store_op(v, e, op);
@@ -144,8 +153,9 @@ __global__ void __launch_bounds__(kBlock) k_env_step(const __grid_constant__ Mod
   OscStats qs = {0, 0};
   if (a.n_sub <= 0) load_op(v, e, op);
   double t = v.clock[e];
+  unsigned qps = v.qp_set[e];
   for (int s = 0; s < a.n_sub; s++) {
-    controller_step<MODE>(mp.phys, mp.ctrl, q, qd, w, act, rows, u, s == a.n_sub - 1 ? &op : nullptr, &st, &qs);
+    controller_step<MODE>(mp.phys, mp.phys_d, ctrl_model<MODE>(mp), q, qd, w, act, rows, u, s == a.n_sub - 1 ? &op : nullptr, &st, &qs, &qps);
     t += 0.0005;  // cassie2d.py:122
   }
   T o18[18], ref9[9], r;
@@ -175,6 +185,7 @@ __global__ void __launch_bounds__(kBlock) k_env_step(const __grid_constant__ Mod
     }
   }
   v.clock[e] = t;
+  v.qp_set[e] = qps;
   store_env(v, e, q, qd, w);
   store_op(v, e, op);
   store_stats(v.stats, v.n, e, st, qs);
@@ -226,6 +237,7 @@ __global__ void __launch_bounds__(kBlock) k_squat(const __grid_constant__ ModelP
   double t = v.clock[e];
   const double ph = phase ? (double)phase[e] : 0.0;
   const double wq = 0.5 * 3.1415;  // squatting.py:9
+  unsigned qps = v.qp_set[e];
   for (int s = 0; s < n_steps; s++) {
     T o18[18];
     op_state_array(op, q, qd, o18);
@@ -234,10 +246,11 @@ __global__ void __launch_bounds__(kBlock) k_squat(const __grid_constant__ ModelP
     const T zt = (T)(0.7 + 0.25 * sn), zdt = (T)(0.25 * cs);
     if (MODE == kModeJacobian) squat_jacobian_action(o18, zt, zdt, act);
     else squat_osc_action(o18, zt, zdt, act);
-    controller_step<MODE>(mp.phys, mp.ctrl, q, qd, w, act, rows, u, &op, &st, &qs);
+    controller_step<MODE>(mp.phys, mp.phys_d, ctrl_model<MODE>(mp), q, qd, w, act, rows, u, &op, &st, &qs, &qps);
     t = t + 0.0005;  // squatting.py:15
   }
   v.clock[e] = t;
+  v.qp_set[e] = qps;
   store_env(v, e, q, qd, w);
   store_op(v, e, op);
   if (n_steps > 0) {

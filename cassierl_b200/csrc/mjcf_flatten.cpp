@@ -613,7 +613,8 @@ bool flatten(const Model3& M, const std::vector<double>& anchor_q, PlanarModel<d
       for (int l = 0; l < 2; l++) for (int x = 0; x < kLegLinks; x++) if (lb[l][x] == root) { L = l; a = x; }
       const V3 cb = P0.xpos[b] + mul(P0.xmat[b], M.bodies[b].ipos);
       double Jx[8], Jz[8], x[kNV];
-      point_jac(m, k, L, a, cb.x - piv0.x, cb.z - piv0.z, Jx, Jz);
+      const double lpx = a >= 0 ? k.px[L][a] : 0.0, lpz = a >= 0 ? k.pz[L][a] : 0.0;
+      point_jac(m, k, L, a, cb.x - piv0.x - lpx, cb.z - piv0.z - lpz, Jx, Jz);
       double s = 0;
       expand_row(Jx, L, x); solve(Mm, Dinv, x); s += dot8_dense(Jx, L, x);
       expand_row(Jz, L, x); solve(Mm, Dinv, x); s += dot8_dense(Jz, L, x);

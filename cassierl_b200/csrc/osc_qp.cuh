@@ -1,12 +1,219 @@
-// placeholder until the device QP lands
+// Operational-space QP controller: the reference's OSC_RBDL::RunPTSC + SolveQP
+// (CassieRL/cassierl src/OSC_RBDL.cpp:114-291, called from Cassie2d::StepOsc,
+// src/Cassie2d/Cassie2d.cpp:179-209), rebuilt as a per-env device routine.
+//
+// The reference assembles a 39-variable / 45-row QP  x = [qdd(13); u(6); beta(20)]  and hands it
+// to qpOASES 3.2.1 (un-vendored).  The same optimum is reached here on a reduced, box-constrained
+// problem:
+//   * qdd is eliminated through the 13 dynamics equalities (OSC_RBDL.cpp:180-184):
+//       qdd = M^-1 (Nc Bt u + Nc Jc^T f + ce),   ce = -Nc bias - gamma;
+//   * planar: the y components of the contact forces have zero Jacobian rows, only their 1e-4
+//     cost remains, so they are 0 at the optimum;
+//   * beta = (x-, x+, z) >= 0 with  x+- <= mu z  (OSC_RBDL.cpp:41-71, mu = 0.5,
+//     RobotInterface.h:64) and cost 1e-4/2 |beta|^2 (OSC_RBDL.cpp:188-201) is equivalent to a
+//     force (fx, fz) in the cone |fx| <= mu fz with cost 1e-4/2 (fx^2 + fz^2); writing the cone by
+//     its two edge generators  f = l1 (mu, 1) + l2 (-mu, 1),  l >= 0  leaves only simple bounds.
+// Result: min 1/2 z'Gz + g'z over z = [u(6); l(8)], u in the motor limits, l >= 0; solved by a
+// block-principal-pivoting method with a masked Cholesky factorisation, in double precision in every
+// build (G = 2 E'WE + reg has a condition number ~1e10; forming it in fp32 would lose the 1e-4
+// regulariser that makes the optimum unique).
 #pragma once
 #include "controllers.cuh"
+
 namespace cassie {
-struct OscStats { int iters; int status; };
-template <typename T>
-CASSIE_HD void osc_control(const PlanarModel<T>& m, const Kin<T>& k, const T* qd, const T a[7], T u[kNU], OscStats* st) {
-  CASSIE_UNROLL
-  for (int i = 0; i < kNU; i++) u[i] = T(0);
-  if (st) { st->iters = 0; st->status = -1; }
+
+struct OscStats { int iters; int status; };  // status 0 = optimal, 1 = iteration cap, 2 = factorisation failed
+
+constexpr int kQpN = 14;
+constexpr int kQpTasks = 11;
+
+// weights: OSC_RBDL.h:92-98 / OSC_RBDL.cpp:32-38 with all four contacts desired (Cassie2d.cpp:199)
+constexpr double kOscWCom = 5.0, kOscWStance = 10.0, kOscWRest = 0.1, kOscWForce = 1e-4, kOscMu = 0.5;
+
+// Box-constrained strictly convex QP   min 1/2 z'Gz + g'z,  lo <= z <= hi   by block principal
+// pivoting (Judice & Pires): every iteration solves the KKT system of the current partition
+// (free / at-lower / at-upper) with a masked Cholesky factorisation and exchanges ALL variables
+// that violate primal or dual feasibility; if the number of violations stops decreasing it falls
+// back to single exchanges, which guarantees termination.  `at_lo` / `at_hi` carry the partition
+// in and out (warm start across steps, like the qpOASES hot start, OSC_RBDL.cpp:278).
+CASSIE_HD void box_qp_solve(const double G[kQpN][kQpN], const double g[kQpN], const double lo[kQpN],
+                            const double hi[kQpN], double z[kQpN], unsigned& at_lo, unsigned& at_hi, int max_iter,
+                            OscStats* st) {
+  double L[kQpN][kQpN], grad[kQpN];
+  double gscale = 1.0;
+  for (int i = 0; i < kQpN; i++) gscale = fmax(gscale, fabs(g[i]));
+  const double dtol = 1e-10 * gscale;
+  int it = 0, status = 1, best = kQpN + 1, budget = 3;
+  for (; it < max_iter; it++) {
+    const unsigned fixed = at_lo | at_hi;
+    for (int i = 0; i < kQpN; i++) z[i] = ((at_lo >> i) & 1u) ? lo[i] : (((at_hi >> i) & 1u) ? hi[i] : 0.0);
+    // rhs_F = -(g_F + G_FB z_B); masked Cholesky: pinned variables become identity rows/columns
+    bool ok = true;
+    for (int i = 0; i < kQpN; i++) {
+      const bool fi = (fixed >> i) & 1u;
+      double rhs = 0.0;
+      if (!fi) {
+        rhs = -g[i];
+        for (int j = 0; j < kQpN; j++)
+          if ((fixed >> j) & 1u) rhs -= G[i][j] * z[j];
+      }
+      grad[i] = rhs;
+      for (int j = 0; j <= i; j++) {
+        const bool fj = (fixed >> j) & 1u;
+        double s = (fi || fj) ? (i == j ? 1.0 : 0.0) : G[i][j];
+        for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
+        if (i == j) {
+          if (!(s > 0.0)) { ok = false; s = 1.0; }
+          L[i][i] = sqrt(s);
+        } else {
+          L[i][j] = s / L[j][j];
+        }
+      }
+    }
+    if (!ok) { status = 2; break; }
+    for (int i = 0; i < kQpN; i++) {
+      double s = grad[i];
+      for (int k = 0; k < i; k++) s -= L[i][k] * grad[k];
+      grad[i] = s / L[i][i];
+    }
+    for (int i = kQpN - 1; i >= 0; i--) {
+      double s = grad[i];
+      for (int k = i + 1; k < kQpN; k++) s -= L[k][i] * grad[k];
+      grad[i] = s / L[i][i];
+      if (!((fixed >> i) & 1u)) z[i] = grad[i];
+    }
+    // violations: free variables outside their bounds, pinned variables with a wrong-sign multiplier
+    unsigned viol = 0u;
+    int nviol = 0, last = -1;
+    for (int i = 0; i < kQpN; i++) {
+      bool bad;
+      if ((fixed >> i) & 1u) {
+        double s = g[i];
+        for (int j = 0; j < kQpN; j++) s += G[i][j] * z[j];
+        bad = ((at_lo >> i) & 1u) ? (s < -dtol) : (s > dtol);
+      } else {
+        const double ptol = 1e-12 * fmax(1.0, fabs(z[i]));
+        bad = z[i] < lo[i] - ptol || z[i] > hi[i] + ptol;
+      }
+      if (bad) { viol |= 1u << i; nviol++; last = i; }
+    }
+    if (nviol == 0) { status = 0; it++; break; }
+    if (nviol < best) { best = nviol; budget = 3; }
+    else if (budget > 0) budget--;
+    else viol = 1u << last;
+    for (int i = 0; i < kQpN; i++) {
+      if (!((viol >> i) & 1u)) continue;
+      if ((fixed >> i) & 1u) { at_lo &= ~(1u << i); at_hi &= ~(1u << i); }
+      else if (z[i] < lo[i]) at_lo |= 1u << i;
+      else at_hi |= 1u << i;
+    }
+  }
+  for (int i = 0; i < kQpN; i++) z[i] = z[i] < lo[i] ? lo[i] : (z[i] > hi[i] ? hi[i] : z[i]);
+  if (st) { st->iters = it; st->status = status; }
 }
+
+// OSC_RBDL::RunPTSC for the planar model.  act = ControllerOsc in memory order (RobotInterface.h:23-28):
+// body_xdd[2], left_xdd[2], right_xdd[2], pitch_add  (x, z pairs; Cassie2d.cpp:185-193).
+template <typename T>
+CASSIE_HD void osc_control(const PlanarModel<T>& m, const Kin<T>& k, const T* qd, const T act[7], T u[kNU], OscStats* st,
+                            unsigned* qp_set = nullptr) {
+  CtrlDyn<T> d;
+  ctrl_dynamics(m, k, qd, d);
+  PivotAcc<T> pa;
+  pivot_accelerations(k, pa);
+  // ---- task rows (OSC_RBDL.cpp:123-144): site Jacobians in J8 layout, leg of each row, Jdot*qd - xdd*
+  T A[kQpTasks][8], e0[kQpTasks];
+  int aleg[kQpTasks];
+  double W[kQpTasks];
+  {
+    T rx, rz;
+    rot(k.c0, k.s0, m.site_off[1][0], m.site_off[1][1], rx, rz);
+    point_jac(m, k, 0, -1, rx, rz, A[0], A[1]);
+    const T w2 = k.w0 * k.w0;
+    e0[0] = -w2 * rx - act[0];
+    e0[1] = -w2 * rz - act[1];
+    aleg[0] = 0; aleg[1] = 0;
+    W[0] = kOscWCom; W[1] = kOscWCom;
+  }
+  CASSIE_UNROLL
+  for (int s = 0; s < 4; s++) {
+    const int L = s / 2, site = 2 + s;
+    T rx, rz;
+    rot(k.c[L][kToe], k.s[L][kToe], m.site_off[site][0], m.site_off[site][1], rx, rz);
+    point_jac(m, k, L, kToe, rx, rz, A[2 + 2 * s], A[3 + 2 * s]);
+    const T w2 = k.w[L][kToe] * k.w[L][kToe];
+    e0[2 + 2 * s] = pa.ax[L][kToe] - w2 * rx - act[2 + 2 * L];
+    e0[3 + 2 * s] = pa.az[L][kToe] - w2 * rz - act[3 + 2 * L];
+    aleg[2 + 2 * s] = L; aleg[3 + 2 * s] = L;
+    W[2 + 2 * s] = kOscWStance; W[3 + 2 * s] = kOscWStance;
+  }
+  CASSIE_UNROLL
+  for (int c = 0; c < 8; c++) A[10][c] = c == 2 ? T(1) : T(0);   // AddQDDIdx(2): pitch (Cassie2d.cpp:41)
+  e0[10] = -act[6];
+  aleg[10] = 0;
+  W[10] = kOscWRest;
+  // ---- P columns: qdd = P z + p0.  Columns 0..5 u, then per contact site (fx, fz)
+  T P[kQpN + 1][kNV];
+  CASSIE_UNROLL
+  for (int a = 0; a < kNU; a++) {
+    CASSIE_UNROLL
+    for (int i = 0; i < kNV; i++) P[a][i] = m.act_dof[a] == i ? m.act_gear[a] : T(0);
+  }
+  CASSIE_UNROLL
+  for (int s = 0; s < 4; s++) {
+    expand_row(A[2 + 2 * s], s / 2, P[kNU + 2 * s]);       // Jc^T e_x of site s  (DynamicState.cpp:57-62)
+    expand_row(A[3 + 2 * s], s / 2, P[kNU + 2 * s + 1]);   // Jc^T e_z
+  }
+  CASSIE_UNROLL
+  for (int i = 0; i < kNV; i++) P[kQpN][i] = -d.bias[i];
+  for (int j = 0; j <= kQpN; j++) {
+    apply_Nc(d, P[j]);
+    if (j == kQpN) {
+      CASSIE_UNROLL
+      for (int i = 0; i < kNV; i++) P[j][i] -= d.gamma[i];
+    }
+    solve(d.LD, d.Dinv, P[j]);
+  }
+  // ---- E = A P (tasks x variables), e0 += A p0 ; then the cone generators l1, l2 per contact
+  double E[kQpTasks][kQpN], r0[kQpTasks];
+  for (int r = 0; r < kQpTasks; r++) {
+    T row[kQpN + 1];
+    for (int j = 0; j <= kQpN; j++) row[j] = dot8_dense(A[r], aleg[r], P[j]);
+    for (int a = 0; a < kNU; a++) E[r][a] = (double)row[a];
+    for (int s = 0; s < 4; s++) {
+      const double ex = (double)row[kNU + 2 * s], ez = (double)row[kNU + 2 * s + 1];
+      E[r][kNU + 2 * s] = kOscMu * ex + ez;
+      E[r][kNU + 2 * s + 1] = -kOscMu * ex + ez;
+    }
+    r0[r] = (double)e0[r] + (double)row[kQpN];
+  }
+  // ---- G = 2 E'WE + 1e-4 T'T,  g = 2 E'W r0   (OSC_RBDL.cpp:186-203)
+  double G[kQpN][kQpN], g[kQpN], lo[kQpN], hi[kQpN], z[kQpN];
+  for (int i = 0; i < kQpN; i++) {
+    for (int j = 0; j <= i; j++) {
+      double s = 0.0;
+      for (int r = 0; r < kQpTasks; r++) s += W[r] * E[r][i] * E[r][j];
+      G[i][j] = 2.0 * s;
+      G[j][i] = 2.0 * s;
+    }
+    double s = 0.0;
+    for (int r = 0; r < kQpTasks; r++) s += W[r] * E[r][i] * r0[r];
+    g[i] = 2.0 * s;
+  }
+  for (int s = 0; s < 4; s++) {
+    const int a = kNU + 2 * s, b = a + 1;
+    G[a][a] += kOscWForce * (kOscMu * kOscMu + 1.0);
+    G[b][b] += kOscWForce * (kOscMu * kOscMu + 1.0);
+    G[a][b] += kOscWForce * (1.0 - kOscMu * kOscMu);
+    G[b][a] += kOscWForce * (1.0 - kOscMu * kOscMu);
+  }
+  for (int a = 0; a < kNU; a++) { lo[a] = (double)m.act_lo[a]; hi[a] = (double)m.act_hi[a]; }
+  for (int i = kNU; i < kQpN; i++) { lo[i] = 0.0; hi[i] = 1e30; }
+  unsigned at_lo = qp_set ? (*qp_set & 0x3fffu) : 0u, at_hi = qp_set ? ((*qp_set >> 14) & 0x3fu) : 0u;
+  box_qp_solve(G, g, lo, hi, z, at_lo, at_hi, 60, st);
+  if (qp_set) *qp_set = at_lo | (at_hi << 14);
+  CASSIE_UNROLL
+  for (int a = 0; a < kNU; a++) u[a] = (T)z[a];
+}
+
 }  // namespace cassie

@@ -23,6 +23,10 @@
 #define CASSIE_UNROLL
 #endif
 
+#ifdef CASSIE_HOST_HARNESS
+extern bool cassie_force_general_path;
+#endif
+
 namespace cassie {
 
 template <typename T> struct Num;
@@ -70,6 +74,7 @@ struct Kin {
   T c0, s0, w0, v0x, v0z;  // pelvis: cos/sin(pitch), pitch rate, pivot velocity
   T c[2][kLegLinks], s[2][kLegLinks];
   T px[2][kLegLinks], pz[2][kLegLinks];
+  T dx[2][kLegLinks], dz[2][kLegLinks];  // pivot - parent's pivot (world axes): exact local lever arms
   T w[2][kLegLinks], vx[2][kLegLinks], vz[2][kLegLinks];
 };
 
@@ -79,13 +84,12 @@ CASSIE_HD void rot(T c, T s, T x, T z, T& ox, T& oz) {
   oz = z * c - x * s;
 }
 
-// mj_kinematics + mj_comVel [EXT] / RBDL UpdateKinematics (DynamicModel.cpp:237-242), planar
+// mj_kinematics + mj_comVel [EXT] / RBDL UpdateKinematics (DynamicModel.cpp:237-242), planar.
+// Split in a position pass (angles -> cos/sin, pivots) and a velocity pass so that the position
+// pass can run in a wider type than the rest of the step (physics_step).
 template <typename T>
-CASSIE_HD void forward_kinematics(const PlanarModel<T>& m, const T* q, const T* qd, Kin<T>& k) {
+CASSIE_HD void fk_positions(const PlanarModel<T>& m, const T* q, Kin<T>& k) {
   Num<T>::sincos_(q[2] - m.pel_ref[2], &k.s0, &k.c0);
-  k.w0 = qd[2];
-  k.v0x = qd[0];
-  k.v0z = qd[1];
   CASSIE_UNROLL
   for (int L = 0; L < 2; L++) {
     T alpha[kLegLinks];
@@ -93,23 +97,55 @@ CASSIE_HD void forward_kinematics(const PlanarModel<T>& m, const T* q, const T* 
     for (int a = 0; a < kLegLinks; a++) {
       const int p = link_parent(a);
       const int dof = 3 + 5 * L + a;
-      T ap, cp, sp, ppx, ppz, wp, vpx, vpz;
-      if (p < 0) {
-        ap = q[2] - m.pel_ref[2]; cp = k.c0; sp = k.s0; ppx = T(0); ppz = T(0);
-        wp = k.w0; vpx = k.v0x; vpz = k.v0z;
-      } else {
-        ap = alpha[p]; cp = k.c[L][p]; sp = k.s[L][p]; ppx = k.px[L][p]; ppz = k.pz[L][p];
-        wp = k.w[L][p]; vpx = k.vx[L][p]; vpz = k.vz[L][p];
-      }
+      T ap, cp, sp, ppx, ppz;
+      if (p < 0) { ap = q[2] - m.pel_ref[2]; cp = k.c0; sp = k.s0; ppx = T(0); ppz = T(0); }
+      else { ap = alpha[p]; cp = k.c[L][p]; sp = k.s[L][p]; ppx = k.px[L][p]; ppz = k.pz[L][p]; }
       alpha[a] = ap + m.sgn[L][a] * q[dof] + m.ang0[L][a];
       Num<T>::sincos_(alpha[a], &k.s[L][a], &k.c[L][a]);
       T dx, dz;
       rot(cp, sp, m.off[L][a][0], m.off[L][a][1], dx, dz);
       k.px[L][a] = ppx + dx;
       k.pz[L][a] = ppz + dz;
+      k.dx[L][a] = dx;
+      k.dz[L][a] = dz;
+    }
+  }
+}
+template <typename T>
+CASSIE_HD void fk_velocities(const PlanarModel<T>& m, const T* qd, Kin<T>& k) {
+  k.w0 = qd[2];
+  k.v0x = qd[0];
+  k.v0z = qd[1];
+  CASSIE_UNROLL
+  for (int L = 0; L < 2; L++) {
+    CASSIE_UNROLL
+    for (int a = 0; a < kLegLinks; a++) {
+      const int p = link_parent(a);
+      const int dof = 3 + 5 * L + a;
+      T wp, vpx, vpz;
+      if (p < 0) { wp = k.w0; vpx = k.v0x; vpz = k.v0z; }
+      else { wp = k.w[L][p]; vpx = k.vx[L][p]; vpz = k.vz[L][p]; }
       k.w[L][a] = wp + m.sgn[L][a] * qd[dof];
-      k.vx[L][a] = vpx + wp * dz;   // w y^ x d = w (d.z, -d.x)
-      k.vz[L][a] = vpz - wp * dx;
+      k.vx[L][a] = vpx + wp * k.dz[L][a];   // w y^ x d = w (d.z, -d.x)
+      k.vz[L][a] = vpz - wp * k.dx[L][a];
+    }
+  }
+}
+template <typename T>
+CASSIE_HD void forward_kinematics(const PlanarModel<T>& m, const T* q, const T* qd, Kin<T>& k) {
+  fk_positions(m, q, k);
+  fk_velocities(m, qd, k);
+}
+template <typename T, typename TG>
+CASSIE_HD void cast_kin_positions(const Kin<TG>& g, Kin<T>& k) {
+  k.c0 = (T)g.c0; k.s0 = (T)g.s0;
+  CASSIE_UNROLL
+  for (int L = 0; L < 2; L++) {
+    CASSIE_UNROLL
+    for (int a = 0; a < kLegLinks; a++) {
+      k.c[L][a] = (T)g.c[L][a]; k.s[L][a] = (T)g.s[L][a];
+      k.px[L][a] = (T)g.px[L][a]; k.pz[L][a] = (T)g.pz[L][a];
+      k.dx[L][a] = (T)g.dx[L][a]; k.dz[L][a] = (T)g.dz[L][a];
     }
   }
 }
@@ -117,8 +153,10 @@ CASSIE_HD void forward_kinematics(const PlanarModel<T>& m, const T* q, const T* 
 // ---------------------------------------------------------------------------------------
 // Mass matrix (lower triangle, structural non-zeros only) + armature.
 // mj_crb [EXT] / RBDL CompositeRigidBodyAlgorithm + rotor inertia (DynamicModel.cpp:267-272).
-// Composite (m, h = m c, Io) per subtree about the pelvis pivot; for hinges i (ancestor) and j:
-//   M_ij = s_i s_j [ Io(j) - (p_i + p_j).h(j) + m(j) p_i.p_j ]
+// Composite (m, h, I) of each subtree is kept ABOUT THAT LINK'S OWN PIVOT and moved to the parent's
+// pivot by the local offset d = p_child - p_parent (parallel-axis), so no large cancelling terms
+// appear in fp32.  For hinge i (pivot p_i) and an ancestor hinge j (pivot p_j):
+//   M_ij = s_i s_j [ I_i + (p_i - p_j) . h_i ],   M_i,x = s_i h_i,z,   M_i,z = -s_i h_i,x.
 template <typename T>
 CASSIE_HD void mass_matrix(const PlanarModel<T>& m, const Kin<T>& k, T M[kNV][kNV]) {
   T tm = m.pel_mass, thx, thz, tI;
@@ -130,38 +168,50 @@ CASSIE_HD void mass_matrix(const PlanarModel<T>& m, const Kin<T>& k, T M[kNV][kN
   }
   CASSIE_UNROLL
   for (int L = 0; L < 2; L++) {
-    T cm[kLegLinks], chx[kLegLinks], chz[kLegLinks], cI[kLegLinks];
+    T cm[kLegLinks], hx[kLegLinks], hz[kLegLinks], cI[kLegLinks];
     CASSIE_UNROLL
     for (int a = 0; a < kLegLinks; a++) {
       T rx, rz;
       rot(k.c[L][a], k.s[L][a], m.com[L][a][0], m.com[L][a][1], rx, rz);
-      const T cx = k.px[L][a] + rx, cz = k.pz[L][a] + rz;
       cm[a] = m.mass[L][a];
-      chx[a] = cm[a] * cx; chz[a] = cm[a] * cz;
-      cI[a] = m.inertia[L][a] + cm[a] * (cx * cx + cz * cz);
+      hx[a] = cm[a] * rx; hz[a] = cm[a] * rz;
+      cI[a] = m.inertia[L][a] + cm[a] * (rx * rx + rz * rz);
     }
-    // accumulate subtrees: toe->tarsus->knee->thigh, rod->thigh
-    cm[kTarsus] += cm[kToe]; chx[kTarsus] += chx[kToe]; chz[kTarsus] += chz[kToe]; cI[kTarsus] += cI[kToe];
-    cm[kKnee] += cm[kTarsus]; chx[kKnee] += chx[kTarsus]; chz[kKnee] += chz[kTarsus]; cI[kKnee] += cI[kTarsus];
-    cm[kThigh] += cm[kKnee] + cm[kRod]; chx[kThigh] += chx[kKnee] + chx[kRod];
-    chz[kThigh] += chz[kKnee] + chz[kRod]; cI[kThigh] += cI[kKnee] + cI[kRod];
-    tm += cm[kThigh]; thx += chx[kThigh]; thz += chz[kThigh]; tI += cI[kThigh];
+    // leaves to root: toe->tarsus->knee->thigh, rod->thigh
+    CASSIE_UNROLL
+    for (int step = 0; step < 4; step++) {
+      const int c = step == 0 ? kToe : (step == 1 ? kTarsus : (step == 2 ? kKnee : kRod));
+      const int p = link_parent(c);
+      const T dx = k.dx[L][c], dz = k.dz[L][c];
+      cI[p] += cI[c] + T(2) * (dx * hx[c] + dz * hz[c]) + cm[c] * (dx * dx + dz * dz);
+      hx[p] += hx[c] + cm[c] * dx;
+      hz[p] += hz[c] + cm[c] * dz;
+      cm[p] += cm[c];
+    }
+    {  // thigh subtree -> whole-robot composite about the pelvis pivot
+      const T dx = k.dx[L][kThigh], dz = k.dz[L][kThigh];
+      tI += cI[kThigh] + T(2) * (dx * hx[kThigh] + dz * hz[kThigh]) + cm[kThigh] * (dx * dx + dz * dz);
+      thx += hx[kThigh] + cm[kThigh] * dx;
+      thz += hz[kThigh] + cm[kThigh] * dz;
+      tm += cm[kThigh];
+    }
     CASSIE_UNROLL
     for (int a = 0; a < kLegLinks; a++) {
       const int i = 3 + 5 * L + a;
-      const T sa = m.sgn[L][a], pax = k.px[L][a], paz = k.pz[L][a];
-      // slides and pitch (pitch pivot = origin of the relative frame, sign +1)
-      M[i][0] = sa * (chz[a] - cm[a] * paz);
-      M[i][1] = -sa * (chx[a] - cm[a] * pax);
-      M[i][2] = sa * (cI[a] - (pax * chx[a] + paz * chz[a]));
+      const T sa = m.sgn[L][a];
+      M[i][0] = sa * hz[a];
+      M[i][1] = -sa * hx[a];
+      M[i][2] = sa * (cI[a] + k.px[L][a] * hx[a] + k.pz[L][a] * hz[a]);
+      M[i][i] = cI[a] + m.armature[i];
+      // walk up the chain accumulating p_a - p_b
+      T lx = T(0), lz = T(0);
+      int b = a;
       CASSIE_UNROLL
-      for (int b = 0; b < kLegLinks; b++) {
-        if (b <= a && link_anc(a, b)) {
-          const T pbx = k.px[L][b], pbz = k.pz[L][b];
-          T v = cI[a] - ((pax + pbx) * chx[a] + (paz + pbz) * chz[a]) + cm[a] * (pax * pbx + paz * pbz);
-          v *= sa * m.sgn[L][b];
-          if (a == b) v += m.armature[i];
-          M[i][3 + 5 * L + b] = v;
+      for (int hop = 0; hop < 3; hop++) {
+        if (link_parent(b) >= 0) {
+          lx += k.dx[L][b]; lz += k.dz[L][b];
+          b = link_parent(b);
+          M[i][3 + 5 * L + b] = sa * m.sgn[L][b] * (cI[a] + lx * hx[a] + lz * hz[a]);
         }
       }
     }
@@ -176,7 +226,8 @@ CASSIE_HD void mass_matrix(const PlanarModel<T>& m, const Kin<T>& k, T M[kNV][kN
 
 // RNE with qdd = 0: bias = C(q,qd) qd + G(q)  (mj_rne [EXT]; RBDL NonlinearEffects,
 // DynamicModel.cpp:320-323).  Planar: angular accelerations vanish, pivots carry the
-// centripetal terms; torques are taken about the pelvis pivot.
+// centripetal terms.  Moments are accumulated about each link's OWN pivot and moved to the parent's
+// pivot by the local offset (no large cancelling terms in fp32).
 template <typename T>
 CASSIE_HD void bias_forces(const PlanarModel<T>& m, const Kin<T>& k, T bias[kNV]) {
   const T g = -m.gravity_z;  // f = m (a_com + g z^)
@@ -196,27 +247,32 @@ CASSIE_HD void bias_forces(const PlanarModel<T>& m, const Kin<T>& k, T bias[kNV]
     CASSIE_UNROLL
     for (int a = 0; a < kLegLinks; a++) {
       const int p = link_parent(a);
-      T apx, apz, wp, ppx, ppz;
-      if (p < 0) { apx = T(0); apz = T(0); wp = k.w0; ppx = T(0); ppz = T(0); }
-      else { apx = ax[p]; apz = az[p]; wp = k.w[L][p]; ppx = k.px[L][p]; ppz = k.pz[L][p]; }
+      T apx, apz, wp;
+      if (p < 0) { apx = T(0); apz = T(0); wp = k.w0; }
+      else { apx = ax[p]; apz = az[p]; wp = k.w[L][p]; }
       const T w2p = wp * wp;
-      ax[a] = apx - w2p * (k.px[L][a] - ppx);
-      az[a] = apz - w2p * (k.pz[L][a] - ppz);
+      ax[a] = apx - w2p * k.dx[L][a];
+      az[a] = apz - w2p * k.dz[L][a];
       T rx, rz;
       rot(k.c[L][a], k.s[L][a], m.com[L][a][0], m.com[L][a][1], rx, rz);
       const T w2 = k.w[L][a] * k.w[L][a];
       fx[a] = m.mass[L][a] * (ax[a] - w2 * rx);
       fz[a] = m.mass[L][a] * (az[a] - w2 * rz + g);
-      const T cx = k.px[L][a] + rx, cz = k.pz[L][a] + rz;
-      n[a] = cz * fx[a] - cx * fz[a];
+      n[a] = rz * fx[a] - rx * fz[a];
     }
-    fx[kTarsus] += fx[kToe]; fz[kTarsus] += fz[kToe]; n[kTarsus] += n[kToe];
-    fx[kKnee] += fx[kTarsus]; fz[kKnee] += fz[kTarsus]; n[kKnee] += n[kTarsus];
-    fx[kThigh] += fx[kKnee] + fx[kRod]; fz[kThigh] += fz[kKnee] + fz[kRod]; n[kThigh] += n[kKnee] + n[kRod];
-    Fx += fx[kThigh]; Fz += fz[kThigh]; N += n[kThigh];
     CASSIE_UNROLL
-    for (int a = 0; a < kLegLinks; a++)
-      bias[3 + 5 * L + a] = m.sgn[L][a] * (n[a] - (k.pz[L][a] * fx[a] - k.px[L][a] * fz[a]));
+    for (int step = 0; step < 4; step++) {
+      const int c = step == 0 ? kToe : (step == 1 ? kTarsus : (step == 2 ? kKnee : kRod));
+      const int p = link_parent(c);
+      n[p] += n[c] + (k.dz[L][c] * fx[c] - k.dx[L][c] * fz[c]);
+      fx[p] += fx[c];
+      fz[p] += fz[c];
+    }
+    N += n[kThigh] + (k.dz[L][kThigh] * fx[kThigh] - k.dx[L][kThigh] * fz[kThigh]);
+    Fx += fx[kThigh];
+    Fz += fz[kThigh];
+    CASSIE_UNROLL
+    for (int a = 0; a < kLegLinks; a++) bias[3 + 5 * L + a] = m.sgn[L][a] * n[a];
   }
   bias[0] = Fx;
   bias[1] = Fz;
@@ -292,19 +348,29 @@ CASSIE_HD T impedance(const T* si, T pos) {  // getimpedance [EXT], margin = 0
   return si[0] + y * (si[1] - si[0]);
 }
 
-// point Jacobian (x row, z row) of a point P (relative to the pelvis pivot) fixed to leg link
-// `a` of leg L;  a = -1: pelvis.  mj_jac [EXT] / RBDL CalcPointJacobian, planar.
+// point Jacobian (x row, z row) of a point fixed to leg link `a` of leg L, given by its lever
+// r = P - p_a from that link's pivot (world axes);  a = -1: pelvis, r from the pelvis pivot.
+// mj_jac [EXT] / RBDL CalcPointJacobian, planar.  Lever arms to the ancestor pivots are built by
+// adding the local pivot-to-pivot offsets, never by subtracting two far-away positions.
 template <typename T>
-CASSIE_HD void point_jac(const PlanarModel<T>& m, const Kin<T>& k, int L, int a, T Px, T Pz, T Jx[8], T Jz[8]) {
-  Jx[0] = T(1); Jx[1] = T(0); Jx[2] = Pz;
-  Jz[0] = T(0); Jz[1] = T(1); Jz[2] = -Px;
+CASSIE_HD void point_jac(const PlanarModel<T>& m, const Kin<T>& k, int L, int a, T rx, T rz, T Jx[8], T Jz[8]) {
   CASSIE_UNROLL
-  for (int b = 0; b < kLegLinks; b++) {
-    const bool on = a >= 0 && (a == b || b == kThigh || (a != kRod && b != kRod && b < a));
-    const T sb = on ? m.sgn[L][b] : T(0);
-    Jx[3 + b] = sb * (Pz - k.pz[L][b]);
-    Jz[3 + b] = -sb * (Px - k.px[L][b]);
+  for (int b = 0; b < kLegLinks; b++) { Jx[3 + b] = T(0); Jz[3 + b] = T(0); }
+  T lx = rx, lz = rz;
+  int b = a;
+  CASSIE_UNROLL
+  for (int hop = 0; hop < 4; hop++) {
+    if (b >= 0) {
+      CASSIE_UNROLL
+      for (int c = 0; c < kLegLinks; c++) {
+        if (c == b) { Jx[3 + c] = m.sgn[L][c] * lz; Jz[3 + c] = -m.sgn[L][c] * lx; }
+      }
+      lx += k.dx[L][b]; lz += k.dz[L][b];
+      b = link_parent(b);
+    }
   }
+  Jx[0] = T(1); Jx[1] = T(0); Jx[2] = lz;
+  Jz[0] = T(0); Jz[1] = T(1); Jz[2] = -lx;
 }
 
 template <typename T>
@@ -342,12 +408,56 @@ CASSIE_HD void kb_from_solref(const PlanarModel<T>& m, const T* solref, const T*
   Bd = T(2) / (bd > T(kMinVal) ? bd : T(kMinVal));
 }
 
+// Position-level constraint violations: the loop-closure anchor mismatch and the signed distances of
+// the collision geoms to the floor.  They are ~1e-4 m differences of ~1 m quantities and get
+// multiplied by the constraint stiffness (1e4 .. 4e4 1/s^2), so the fp32 build evaluates them from
+// the position pass in double (physics_step) -- the dominant single-step error otherwise.
+template <typename T>
+struct ConPos {
+  T eq_rx[2], eq_rz[2];
+  T sph_dist, cap_dist[kNumCaps][2];
+};
+template <typename TG, typename T>
+CASSIE_HD void constraint_positions(const PlanarModel<TG>& m, const Kin<TG>& k, TG body_z, ConPos<T>& cp) {
+  CASSIE_UNROLL
+  for (int L = 0; L < 2; L++) {
+    TG ax, az, bx, bz;
+    rot(k.c[L][kRod], k.s[L][kRod], m.eq_a1[L][0], m.eq_a1[L][1], ax, az);
+    rot(k.c[L][kTarsus], k.s[L][kTarsus], m.eq_a2[L][0], m.eq_a2[L][1], bx, bz);
+    // (p_rod + a) - (p_tarsus + b),  p_rod - p_tarsus = d_rod - d_knee - d_tarsus
+    cp.eq_rx[L] = (T)((k.dx[L][kRod] - k.dx[L][kKnee] - k.dx[L][kTarsus]) + (ax - bx));
+    cp.eq_rz[L] = (T)((k.dz[L][kRod] - k.dz[L][kKnee] - k.dz[L][kTarsus]) + (az - bz));
+  }
+  const TG height = body_z - m.pel_ref[1] + m.pel_org[1];  // world z of the pelvis pivot
+  {
+    TG cx, cz;
+    rot(k.c0, k.s0, m.sph_c[0], m.sph_c[1], cx, cz);
+    cp.sph_dist = (T)(height + cz - m.sph_r);
+  }
+  CASSIE_UNROLL
+  for (int L = 0; L < 2; L++) {
+    CASSIE_UNROLL
+    for (int g = 0; g < 4; g++) {
+      const int cap = 4 * L + g;
+      CASSIE_UNROLL
+      for (int e = 0; e < 2; e++) {
+        TG ex, ez;
+        const TG* ep = e ? m.cap_from[cap] : m.cap_to[cap];
+        rot(k.c[L][g], k.s[L][g], ep[0], ep[1], ex, ez);
+        cp.cap_dist[cap][e] = (T)(height + k.pz[L][g] + ez - m.cap_r[cap]);
+      }
+    }
+  }
+}
+
 // mj_collision + mj_makeConstraint + mj_makeImpedance [EXT], canonical row order:
 // connects (L, R), joint limits (dof order), contacts (pelvis sphere, then per capsule the 'to'
 // end before the 'from' end).  Returns the public contact bit mask.
 template <typename T>
-CASSIE_HD unsigned int make_rows(const PlanarModel<T>& m, const Kin<T>& k, const T* q, const T* qd, Rows<T>& r) {
+CASSIE_HD unsigned int make_rows(const PlanarModel<T>& m, const Kin<T>& k, const ConPos<T>& cp, const T* q, const T* qd,
+                                  Rows<T>& r, int* nlimit) {
   r.n = 0;
+  int nlim = 0;
   T K, Bd;
   // ---- connects
   kb_from_solref(m, m.eq_solref, m.eq_solimp, K, Bd);
@@ -356,14 +466,12 @@ CASSIE_HD unsigned int make_rows(const PlanarModel<T>& m, const Kin<T>& k, const
     T ax, az, bx, bz;
     rot(k.c[L][kRod], k.s[L][kRod], m.eq_a1[L][0], m.eq_a1[L][1], ax, az);
     rot(k.c[L][kTarsus], k.s[L][kTarsus], m.eq_a2[L][0], m.eq_a2[L][1], bx, bz);
-    const T P1x = k.px[L][kRod] + ax, P1z = k.pz[L][kRod] + az;
-    const T P2x = k.px[L][kTarsus] + bx, P2z = k.pz[L][kTarsus] + bz;
     T J1x[8], J1z[8], J2x[8], J2z[8];
-    point_jac(m, k, L, kRod, P1x, P1z, J1x, J1z);
-    point_jac(m, k, L, kTarsus, P2x, P2z, J2x, J2z);
+    point_jac(m, k, L, kRod, ax, az, J1x, J1z);
+    point_jac(m, k, L, kTarsus, bx, bz, J2x, J2z);
     CASSIE_UNROLL
     for (int c = 0; c < 8; c++) { J1x[c] -= J2x[c]; J1z[c] -= J2z[c]; }
-    const T rx = P1x - P2x, rz = P1z - P2z;
+    const T rx = cp.eq_rx[L], rz = cp.eq_rz[L];
     const T imp = impedance(m.eq_solimp, Num<T>::sqrt_(rx * rx + rz * rz));
     push_row(r, J1x, L, kRowEq, m.eq_diag[L], imp, K, Bd, rx, qd);
     push_row(r, J1z, L, kRowEq, m.eq_diag[L], imp, K, Bd, rz, qd);
@@ -383,6 +491,7 @@ CASSIE_HD unsigned int make_rows(const PlanarModel<T>& m, const Kin<T>& k, const
           for (int c = 0; c < 8; c++) J8[c] = T(0);
           J8[3 + (j - 3) % 5] = side ? T(-1) : T(1);
           push_row(r, J8, (j - 3) / 5, kRowLimit, m.lim_diag[j], impedance(m.lim_solimp, dist), K, Bd, dist, qd);
+          nlim++;
         }
       }
     }
@@ -390,15 +499,13 @@ CASSIE_HD unsigned int make_rows(const PlanarModel<T>& m, const Kin<T>& k, const
   // ---- floor contacts (plane z = 0, normal +z).  Elliptic friction rows: K = 0, pos = 0.
   unsigned int mask = 0;
   kb_from_solref(m, m.con_solref, m.con_solimp, K, Bd);
-  const T height = q[1] - m.pel_ref[1] + m.pel_org[1];  // world z of the pelvis pivot
   {
     T cx, cz;
     rot(k.c0, k.s0, m.sph_c[0], m.sph_c[1], cx, cz);
-    const T dist = height + cz - m.sph_r;
+    const T dist = cp.sph_dist;
     if (!(dist > T(0))) {
       T Jx[8], Jz[8];
-      const T Pz = T(0.5) * dist - height;
-      point_jac(m, k, 0, -1, cx, Pz, Jx, Jz);
+      point_jac(m, k, 0, -1, cx, cz - m.sph_r - T(0.5) * dist, Jx, Jz);
       const T imp = impedance(m.con_solimp, dist);
       push_row(r, Jz, 0, kRowNormal, m.sph_diag, imp, K, Bd, dist, qd);
       push_row(r, Jx, 0, kRowTangent, m.sph_diag, imp, T(0), Bd, T(0), qd);
@@ -415,11 +522,10 @@ CASSIE_HD unsigned int make_rows(const PlanarModel<T>& m, const Kin<T>& k, const
         T ex, ez;
         const T* ep = e ? m.cap_from[cap] : m.cap_to[cap];
         rot(k.c[L][g], k.s[L][g], ep[0], ep[1], ex, ez);
-        const T Px = k.px[L][g] + ex;
-        const T dist = height + k.pz[L][g] + ez - m.cap_r[cap];
+        const T dist = cp.cap_dist[cap][e];
         if (!(dist > T(0))) {
           T Jx[8], Jz[8];
-          point_jac(m, k, L, g, Px, T(0.5) * dist - height, Jx, Jz);
+          point_jac(m, k, L, g, ex, ez - m.cap_r[cap] - T(0.5) * dist, Jx, Jz);
           const T imp = impedance(m.con_solimp, dist);
           push_row(r, Jz, L, kRowNormal, m.cap_diag[cap], imp, K, Bd, dist, qd);
           push_row(r, Jx, L, kRowTangent, m.cap_diag[cap], imp, T(0), Bd, T(0), qd);
@@ -428,6 +534,7 @@ CASSIE_HD unsigned int make_rows(const PlanarModel<T>& m, const Kin<T>& k, const
       }
     }
   }
+  if (nlimit) *nlimit = nlim;
   return mask;
 }
 
@@ -531,40 +638,12 @@ struct StepStats {
   unsigned int contact_mask;
 };
 
-// One mj_step [EXT] (Cassie2d.cpp:92): forward dynamics, constraint solve, semi-implicit Euler
-// with implicit joint damping.  q, qd, warm are updated in place; u is in ctrl units.
+// ---------------------------------------------------------------------------------------
+// Constraint solve, general path: any number of rows (<= kMaxRows), A and f in thread-local
+// memory.  Returns the PGS sweep count and qfrc_constraint = J^T f in fc.
 template <typename T>
-CASSIE_HD void physics_step(const PlanarModel<T>& m, T q[kNV], T qd[kNV], T warm[kNV], const T u[kNU],
-                            Rows<T>& r, StepStats* st) {
-  Kin<T> k;
-  forward_kinematics(m, q, qd, k);
-  T M[kNV][kNV], LD[kNV][kNV], Dinv[kNV];
-  mass_matrix(m, k, M);
-  T fs[kNV];  // qfrc_smooth = passive - bias + actuator
-  bias_forces(m, k, fs);
-  CASSIE_UNROLL
-  for (int i = 0; i < kNV; i++) fs[i] = -fs[i] - m.damping[i] * qd[i];
-  CASSIE_UNROLL
-  for (int a = 0; a < kNU; a++) {
-    T c = u[a];
-    c = c < m.act_lo[a] ? m.act_lo[a] : (c > m.act_hi[a] ? m.act_hi[a] : c);
-    CASSIE_UNROLL
-    for (int i = 3; i < kNV; i++)
-      if (m.act_dof[a] == i) fs[i] += m.act_gear[a] * c;
-  }
-  CASSIE_UNROLL
-  for (int i = 0; i < kNV; i++) {
-    CASSIE_UNROLL
-    for (int j = 0; j < kNV; j++)
-      if (dof_anc(i, j)) LD[i][j] = M[i][j];
-  }
-  factor(LD, Dinv);
-  T qs[kNV];  // qacc_smooth
-  CASSIE_UNROLL
-  for (int i = 0; i < kNV; i++) qs[i] = fs[i];
-  solve(LD, Dinv, qs);
-
-  const unsigned int mask = make_rows(m, k, q, qd, r);
+CASSIE_HD int constraint_solve_general(const PlanarModel<T>& m, Rows<T>& r, const T LD[kNV][kNV], const T Dinv[kNV],
+                                       const T qs[kNV], const T warm[kNV], T fc[kNV]) {
   const int n = r.n;
   // b = J qacc_smooth - aref ;  A = J M^-1 J^T + diag(R)
   for (int i = 0; i < n; i++) {
@@ -596,8 +675,6 @@ CASSIE_HD void physics_step(const PlanarModel<T>& m, T q[kNV], T qd[kNV], T warm
       for (int i = 0; i < n; i++) r.f[i] = T(0);
   }
   const int sweeps = solve_pgs(m, r);
-  // qfrc_constraint = J^T f ; qacc = qacc_smooth + M^-1 qfrc_constraint
-  T fc[kNV];
   CASSIE_UNROLL
   for (int i = 0; i < kNV; i++) fc[i] = T(0);
   for (int i = 0; i < n; i++) {
@@ -611,6 +688,206 @@ CASSIE_HD void physics_step(const PlanarModel<T>& m, T q[kNV], T qd[kNV], T warm
       fc[8 + b] += leg ? v : T(0);
     }
   }
+  return sweeps;
+}
+
+// ---------------------------------------------------------------------------------------
+// Constraint solve, fast path: the standing / squatting / walking regime has the 4 connect rows
+// and at most 4 floor contacts (no joint-limit rows), i.e. <= 12 rows in the fixed order
+// [eq Lx, eq Lz, eq Rx, eq Rz, (normal, tangent) x 4].  Everything -- A (78 symmetric entries), b,
+// f -- then lives in registers and the PGS sweep is fully unrolled and branch-free; missing
+// contact pairs are padded with inert rows (J = 0, A_ii = 1, b = 0).  Same arithmetic as the
+// general path (mj_solPGS [EXT]) except that 1/A_ii is precomputed.
+constexpr int kFastRows = 12;
+CASSIE_HD constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+
+template <typename T>
+CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T LD[kNV][kNV], const T Dinv[kNV],
+                                    const T qs[kNV], const T warm[kNV], T fc[kNV]) {
+  const int n = r.n;
+  for (int i = n; i < kFastRows; i++) {  // inert padding
+    CASSIE_UNROLL
+    for (int c = 0; c < 8; c++) r.J[i][c] = T(0);
+    r.leg[i] = 0;
+    r.R[i] = T(1);
+    r.b[i] = T(0);
+  }
+  T A[kFastRows * (kFastRows + 1) / 2], b[kFastRows], f[kFastRows], jar[kFastRows];
+  CASSIE_UNROLL
+  for (int i = 0; i < kFastRows; i++) {
+    T Bi[kNV];
+    expand_row(r.J[i], r.leg[i], Bi);
+    const T maref = r.b[i];
+    b[i] = maref + dot8_dense(r.J[i], r.leg[i], qs);
+    jar[i] = maref + dot8_dense(r.J[i], r.leg[i], warm);
+    if (i < 4 || i < n) solve(LD, Dinv, Bi);
+    CASSIE_UNROLL
+    for (int j = 0; j < kFastRows; j++)
+      if (j <= i) A[tri(i, j)] = dot8_dense(r.J[j], r.leg[j], Bi);
+    A[tri(i, i)] += r.R[i];
+  }
+  // warm start (mj_constraintUpdate [EXT] on jar = J qacc_warmstart - aref)
+  CASSIE_UNROLL
+  for (int i = 0; i < 4; i++) f[i] = -jar[i] / r.R[i];
+  {
+    const T mu = m.con_mu / Num<T>::sqrt_(m.impratio);
+    CASSIE_UNROLL
+    for (int i = 4; i < kFastRows; i += 2) {
+      const T N = jar[i] * mu, U1 = jar[i + 1] * m.con_mu, Tn = Num<T>::abs_(U1);
+      const T D0 = T(1) / r.R[i], D1 = T(1) / r.R[i + 1];
+      T f0, f1;
+      if (N >= mu * Tn || (Tn <= T(0) && N >= T(0))) { f0 = T(0); f1 = T(0); }
+      else if (mu * N + Tn <= T(0) || (Tn <= T(0) && N < T(0))) { f0 = -D0 * jar[i]; f1 = -D1 * jar[i + 1]; }
+      else {
+        T den = mu * mu * (T(1) + mu * mu);
+        const T Dm = D0 / (den > T(kMinVal) ? den : T(kMinVal));
+        f0 = -Dm * (N - mu * Tn) * mu;
+        f1 = -f0 / Tn * U1 * m.con_mu;
+      }
+      f[i] = f0; f[i + 1] = f1;
+    }
+  }
+  {
+    T cost = T(0);
+    CASSIE_UNROLL
+    for (int i = 0; i < kFastRows; i++) {
+      T s = T(0);
+      CASSIE_UNROLL
+      for (int c = 0; c < kFastRows; c++) s += A[tri(i, c)] * f[c];
+      cost += f[i] * (T(0.5) * s + b[i]);
+    }
+    if (cost > T(0)) {
+      CASSIE_UNROLL
+      for (int i = 0; i < kFastRows; i++) f[i] = T(0);
+    }
+  }
+  T inv[kFastRows];
+  CASSIE_UNROLL
+  for (int i = 0; i < kFastRows; i++) inv[i] = T(1) / A[tri(i, i)];
+  const T scale = T(1) / (m.meaninertia * T(kNV));
+  const T inv_mu = T(1) / m.con_mu;
+  int iter = 0;
+  while (iter < m.iterations) {
+    T improvement = T(0);
+    CASSIE_UNROLL
+    for (int i = 0; i < 4; i++) {  // equality rows: unbounded
+      T res = b[i];
+      CASSIE_UNROLL
+      for (int c = 0; c < kFastRows; c++) res += A[tri(i, c)] * f[c];
+      const T fn = f[i] - res * inv[i];
+      const T d = fn - f[i];
+      const T change = T(0.5) * d * d * A[tri(i, i)] + d * res;
+      const bool keep = !(change > T(1e-10));
+      f[i] = keep ? fn : f[i];
+      improvement -= keep ? change : T(0);
+    }
+    CASSIE_UNROLL
+    for (int i = 4; i < kFastRows; i += 2) {  // elliptic contact: normal + one tangent
+      T res0 = b[i], res1 = b[i + 1];
+      CASSIE_UNROLL
+      for (int c = 0; c < kFastRows; c++) { res0 += A[tri(i, c)] * f[c]; res1 += A[tri(i + 1, c)] * f[c]; }
+      const T old0 = f[i], old1 = f[i + 1];
+      const T A00 = A[tri(i, i)], A01 = A[tri(i + 1, i)], A11 = A[tri(i + 1, i + 1)];
+      // (a) normal / ray update
+      const T fa = old0 - res0 * inv[i];
+      const T denom = old0 * (A00 * old0 + A01 * old1) + old1 * (A01 * old0 + A11 * old1);
+      T x = -(old0 * res0 + old1 * res1) / (denom >= T(kMinVal) ? denom : T(1));
+      x = denom >= T(kMinVal) ? x : T(0);
+      x = (old0 + x * old0 < T(0)) ? T(-1) : x;
+      const bool low = old0 < T(kMinVal);
+      T f0 = low ? (fa < T(0) ? T(0) : fa) : old0 + x * old0;
+      // (b) friction update with the normal force fixed (mju_QCQP2 collapses to a clamp)
+      const T bc = res1 - A11 * old1 + A01 * (f0 - old0);
+      T v = -bc * inv[i + 1];
+      const T vs = v * inv_mu;
+      const T lim = m.con_mu * f0;
+      v = (vs * vs - f0 * f0 >= T(1e-10)) ? (v > T(0) ? lim : -lim) : v;
+      T f1 = f0 < T(kMinVal) ? T(0) : v;
+      const T d0 = f0 - old0, d1 = f1 - old1;
+      const T change = T(0.5) * (d0 * (A00 * d0 + A01 * d1) + d1 * (A01 * d0 + A11 * d1)) + d0 * res0 + d1 * res1;
+      const bool keep = !(change > T(1e-10));
+      f[i] = keep ? f0 : old0;
+      f[i + 1] = keep ? f1 : old1;
+      improvement -= keep ? change : T(0);
+    }
+    iter++;
+    if (improvement * scale < m.tolerance) break;
+  }
+  CASSIE_UNROLL
+  for (int i = 0; i < kNV; i++) fc[i] = T(0);
+  CASSIE_UNROLL
+  for (int i = 0; i < kFastRows; i++) {
+    const T fi = f[i];
+    const int leg = r.leg[i];
+    fc[0] += r.J[i][0] * fi; fc[1] += r.J[i][1] * fi; fc[2] += r.J[i][2] * fi;
+    CASSIE_UNROLL
+    for (int bb = 0; bb < kLegLinks; bb++) {
+      const T v = r.J[i][3 + bb] * fi;
+      fc[3 + bb] += leg ? T(0) : v;
+      fc[8 + bb] += leg ? v : T(0);
+    }
+  }
+  return iter;
+}
+
+// One mj_step [EXT] (Cassie2d.cpp:92): forward dynamics, constraint solve, semi-implicit Euler
+// with implicit joint damping.  q, qd, warm are updated in place; u is in ctrl units.
+// TG = type of the position pass (angles -> sin/cos -> pivots -> constraint violations): double in
+// the fp32 build (mg = the same model in double), T in the fp64 build.
+template <typename T, typename TG>
+CASSIE_HD void physics_step(const PlanarModel<T>& m, const PlanarModel<TG>& mg, T q[kNV], T qd[kNV], T warm[kNV],
+                            const T u[kNU], Rows<T>& r, StepStats* st) {
+  Kin<T> k;
+  ConPos<T> cp;
+  {
+    TG qg[kNV];
+    CASSIE_UNROLL
+    for (int i = 0; i < kNV; i++) qg[i] = (TG)q[i];
+    Kin<TG> kg;
+    fk_positions(mg, qg, kg);
+    constraint_positions(mg, kg, qg[1], cp);
+    cast_kin_positions(kg, k);
+  }
+  fk_velocities(m, qd, k);
+  T M[kNV][kNV], LD[kNV][kNV], Dinv[kNV];
+  mass_matrix(m, k, M);
+  T fs[kNV];  // qfrc_smooth = passive - bias + actuator
+  bias_forces(m, k, fs);
+  CASSIE_UNROLL
+  for (int i = 0; i < kNV; i++) fs[i] = -fs[i] - m.damping[i] * qd[i];
+  CASSIE_UNROLL
+  for (int a = 0; a < kNU; a++) {
+    T c = u[a];
+    c = c < m.act_lo[a] ? m.act_lo[a] : (c > m.act_hi[a] ? m.act_hi[a] : c);
+    CASSIE_UNROLL
+    for (int i = 3; i < kNV; i++)
+      if (m.act_dof[a] == i) fs[i] += m.act_gear[a] * c;
+  }
+  CASSIE_UNROLL
+  for (int i = 0; i < kNV; i++) {
+    CASSIE_UNROLL
+    for (int j = 0; j < kNV; j++)
+      if (dof_anc(i, j)) LD[i][j] = M[i][j];
+  }
+  factor(LD, Dinv);
+  T qs[kNV];  // qacc_smooth
+  CASSIE_UNROLL
+  for (int i = 0; i < kNV; i++) qs[i] = fs[i];
+  solve(LD, Dinv, qs);
+
+  int nlimit = 0;
+  const unsigned int mask = make_rows(m, k, cp, q, qd, r, &nlimit);
+  const int n = r.n;
+  T fc[kNV];  // qfrc_constraint = J^T f
+  int sweeps;
+#ifdef CASSIE_HOST_HARNESS  // test hook: lets the harness exercise / count the general path on small row counts
+  const bool fast_ok = !cassie_force_general_path;
+#else
+  const bool fast_ok = true;
+#endif
+  if (fast_ok && nlimit == 0 && n <= kFastRows) sweeps = constraint_solve_fast(m, r, LD, Dinv, qs, warm, fc);
+  else sweeps = constraint_solve_general(m, r, LD, Dinv, qs, warm, fc);
+  // qacc = qacc_smooth + M^-1 qfrc_constraint
   T dq[kNV];
   CASSIE_UNROLL
   for (int i = 0; i < kNV; i++) dq[i] = fc[i];

@@ -78,9 +78,11 @@ class Harness:
         return dict(u=u, op=op, traj=traj, mask=mk, qp=qp)
 
     def squat(self, mode, n, phase, q, qd, warm, f32=False):
-        traj = np.zeros((n, 26)); u = np.zeros((n, 6))
+        traj = np.zeros((n, 26)); u = np.zeros((n, 6)); qp = np.zeros((n, 2), np.int32)
         fn = self.L.hh_squat_f32 if f32 else self.L.hh_squat_f64
-        fn(int(mode), n, ct.c_double(phase), self.p(q), self.p(qd), self.p(warm), self.p(traj), self.p(u))
+        fn(int(mode), n, ct.c_double(phase), self.p(q), self.p(qd), self.p(warm), self.p(traj), self.p(u),
+           qp.ctypes.data_as(ct.POINTER(ct.c_int)))
+        self.last_qp = qp
         return traj, u
 
     def ctrl_dynamics(self, q, qd):

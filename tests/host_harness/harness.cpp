@@ -2,12 +2,14 @@
 // cassierl_b200/csrc) and the host flattener for the CPU, so that `-m "not gpu"` tests can
 // check the kernel's arithmetic against the oracle without a GPU.  Never loaded by the
 // product package.
+#define CASSIE_HOST_HARNESS 1
 #include <cstring>
 #include <string>
 #include "../../cassierl_b200/csrc/mjcf_flatten.h"
 #include "../../cassierl_b200/csrc/cassie_step.cuh"
 
 using namespace cassie;
+bool cassie_force_general_path = false;
 
 // ---- operation-counting scalar: the engine instantiated on it yields the exact algorithmic
 // FLOP count of one step (bench.py's roofline numerator)
@@ -56,7 +58,7 @@ static void run_steps(int n, double* q, double* qd, double* warm, const double* 
   for (int s = 0; s < n; s++) {
     for (int i = 0; i < kNU; i++) tu[i] = (T)u[s * kNU + i];
     StepStats st;
-    physics_step(m, tq, tv, tw, tu, rows, &st);
+    physics_step(m, g_models.phys, tq, tv, tw, tu, rows, &st);
     if (nrows) nrows[s] = st.nrows;
     if (sweeps) sweeps[s] = st.sweeps;
     if (mask) mask[s] = st.contact_mask;
@@ -64,10 +66,12 @@ static void run_steps(int n, double* q, double* qd, double* warm, const double* 
   for (int i = 0; i < kNV; i++) { q[i] = tq[i]; qd[i] = tv[i]; warm[i] = tw[i]; }
 }
 
-template <typename T>
+template <typename T, typename TC>
 static void ctrl_step(int mode, int n, double* q, double* qd, double* warm, const double* act, int adim,
                       double* u_out, double* op_out, double* traj_out, unsigned* mask_out, int* qp_out) {
-  PlanarModel<T> mp = cast_model<T>(g_models.phys), mc = cast_model<T>(g_models.ctrl);
+  PlanarModel<T> mp = cast_model<T>(g_models.phys);
+  PlanarModel<TC> mc = cast_model<TC>(g_models.ctrl);
+  unsigned qp_set = 0u;
   T tq[kNV], tv[kNV], tw[kNV];
   for (int i = 0; i < kNV; i++) { tq[i] = (T)q[i]; tv[i] = (T)qd[i]; tw[i] = (T)warm[i]; }
   static thread_local Rows<T> rows;
@@ -77,7 +81,7 @@ static void ctrl_step(int mode, int n, double* q, double* qd, double* warm, cons
     OpState<T> op;
     StepStats st;
     OscStats qs = {0, 0};
-    controller_step_dyn(mp, mc, mode, tq, tv, tw, a, rows, u, &op, &st, &qs);
+    controller_step_dyn(mp, g_models.phys, mc, mode, tq, tv, tw, a, rows, u, &op, &st, &qs, &qp_set);
     if (u_out) for (int i = 0; i < kNU; i++) u_out[s * kNU + i] = u[i];
     if (op_out) {
       T o[18];
@@ -92,17 +96,20 @@ static void ctrl_step(int mode, int n, double* q, double* qd, double* warm, cons
 }
 
 // the squatting.py loop (squatting.py:8-16): mode 2 = standing_controller_jacobian, 3 = _osc
-template <typename T>
-static void squat(int mode, int n, double phase, double* q, double* qd, double* warm, double* traj_out, double* u_out) {
-  PlanarModel<T> mp = cast_model<T>(g_models.phys), mc = cast_model<T>(g_models.ctrl);
+template <typename T, typename TC>
+static void squat(int mode, int n, double phase, double* q, double* qd, double* warm, double* traj_out, double* u_out, int* qp_out) {
+  PlanarModel<T> mp = cast_model<T>(g_models.phys);
+  PlanarModel<TC> mc = cast_model<TC>(g_models.ctrl);
+  unsigned qp_set = 0u;
   T tq[kNV], tv[kNV], tw[kNV];
   for (int i = 0; i < kNV; i++) { tq[i] = (T)q[i]; tv[i] = (T)qd[i]; tw[i] = (T)warm[i]; }
   static thread_local Rows<T> rows;
   OpState<T> op;
   {
+    PlanarModel<T> mct = cast_model<T>(g_models.ctrl);
     Kin<T> kc;
-    forward_kinematics(mc, tq, tv, kc);
-    op_state_from_kin(mc, kc, tq, op);
+    forward_kinematics(mct, tq, tv, kc);
+    op_state_from_kin(mct, kc, tq, op);
   }
   const double w = 0.5 * 3.1415;
   double t = 0.0;
@@ -112,7 +119,9 @@ static void squat(int mode, int n, double phase, double* q, double* qd, double* 
     const T zt = (T)(0.7 + 0.25 * sin(w * t + phase)), zdt = (T)(0.25 * cos(w * t + phase));
     if (mode == kModeJacobian) squat_jacobian_action(o, zt, zdt, a);
     else squat_osc_action(o, zt, zdt, a);
-    controller_step_dyn(mp, mc, mode, tq, tv, tw, a, rows, u, &op, (StepStats*)nullptr);
+    OscStats qs = {0, 0};
+    controller_step_dyn(mp, g_models.phys, mc, mode, tq, tv, tw, a, rows, u, &op, (StepStats*)nullptr, &qs, &qp_set);
+    if (qp_out) { qp_out[2 * s] = qs.iters; qp_out[2 * s + 1] = qs.status; }
     t = t + 0.0005;
     if (traj_out) for (int i = 0; i < kNV; i++) { traj_out[s * 26 + i] = tq[i]; traj_out[s * 26 + 13 + i] = tv[i]; }
     if (u_out) for (int i = 0; i < kNU; i++) u_out[s * kNU + i] = u[i];
@@ -125,9 +134,11 @@ static_assert(sizeof(PlanarModel<CountD>) == sizeof(PlanarModel<double>), "Count
 extern "C" {
 
 // exact operation counts of ONE Step* call at the given state: out[0..5] = add/sub, mul, div, sqrt,
-// transcendental (sincos/pow/exp), compare ; out[6] = constraint rows, out[7] = PGS sweeps
+// transcendental (sincos/pow/exp), compare ; out[6] = constraint rows, out[7] = PGS sweeps,
+// out[8] = QP iterations (the QP itself runs in plain double and is counted analytically), out[9] = partition
 void hh_count_ops(int mode, const double* q, const double* qd, const double* warm, const double* act, int adim, long* out) {
-  PlanarModel<CountD> mp, mc;
+  PlanarModel<CountD> mp, mc, mg;
+  std::memcpy((void*)&mg, &g_models.phys, sizeof(mg));
   std::memcpy((void*)&mp, &g_models.phys, sizeof(mp));
   std::memcpy((void*)&mc, &g_models.ctrl, sizeof(mc));
   CountD tq[kNV], tv[kNV], tw[kNV], a[8], u[kNU];
@@ -137,11 +148,15 @@ void hh_count_ops(int mode, const double* q, const double* qd, const double* war
   OpState<CountD> op;
   StepStats st;
   g_ops = OpCount();
-  controller_step_dyn(mp, mc, mode, tq, tv, tw, a, rows, u, &op, &st);
+  OscStats qs = {0, 0};
+  unsigned qp_set = (unsigned)out[8];   // in: warm-start partition, out: QP iterations
+  controller_step_dyn(mp, mg, mc, mode, tq, tv, tw, a, rows, u, &op, &st, &qs, &qp_set);
+  out[8] = qs.iters; out[9] = qp_set;
   out[0] = g_ops.add; out[1] = g_ops.mul; out[2] = g_ops.div; out[3] = g_ops.sqrt_; out[4] = g_ops.trig; out[5] = g_ops.cmp;
   out[6] = st.nrows; out[7] = st.sweeps;
 }
 
+void hh_force_general_path(int on) { cassie_force_general_path = on != 0; }
 int hh_load(const char* path) { return flatten_mjcf_file(path, &g_models, &g_err) ? 0 : -1; }
 const char* hh_error() { return g_err.c_str(); }
 const void* hh_model(int ctrl) { return ctrl ? &g_models.ctrl : &g_models.phys; }
@@ -195,16 +210,19 @@ void hh_ctrl_dynamics(const double* q, const double* qd, double* bias, double* J
 // GetOperationalSpaceState a caller would read AFTER each step; traj_out [n][26] qpos,qvel
 void hh_ctrl_steps_f64(int mode, int n, double* q, double* qd, double* warm, const double* act, int adim,
                        double* u_out, double* op_out, double* traj_out, unsigned* mask_out, int* qp_out) {
-  ctrl_step<double>(mode, n, q, qd, warm, act, adim, u_out, op_out, traj_out, mask_out, qp_out);
+  ctrl_step<double, double>(mode, n, q, qd, warm, act, adim, u_out, op_out, traj_out, mask_out, qp_out);
 }
 void hh_ctrl_steps_f32(int mode, int n, double* q, double* qd, double* warm, const double* act, int adim,
                        double* u_out, double* op_out, double* traj_out, unsigned* mask_out, int* qp_out) {
-  ctrl_step<float>(mode, n, q, qd, warm, act, adim, u_out, op_out, traj_out, mask_out, qp_out);
+  // the fp32 product build runs the OSC controller in double (cassie_step.cuh)
+  if (mode == kModeOsc) ctrl_step<float, double>(mode, n, q, qd, warm, act, adim, u_out, op_out, traj_out, mask_out, qp_out);
+  else ctrl_step<float, float>(mode, n, q, qd, warm, act, adim, u_out, op_out, traj_out, mask_out, qp_out);
 }
-void hh_squat_f64(int mode, int n, double phase, double* q, double* qd, double* warm, double* traj_out, double* u_out) {
-  squat<double>(mode, n, phase, q, qd, warm, traj_out, u_out);
+void hh_squat_f64(int mode, int n, double phase, double* q, double* qd, double* warm, double* traj_out, double* u_out, int* qp_out) {
+  squat<double, double>(mode, n, phase, q, qd, warm, traj_out, u_out, qp_out);
 }
-void hh_squat_f32(int mode, int n, double phase, double* q, double* qd, double* warm, double* traj_out, double* u_out) {
-  squat<float>(mode, n, phase, q, qd, warm, traj_out, u_out);
+void hh_squat_f32(int mode, int n, double phase, double* q, double* qd, double* warm, double* traj_out, double* u_out, int* qp_out) {
+  if (mode == kModeOsc) squat<float, double>(mode, n, phase, q, qd, warm, traj_out, u_out, qp_out);
+  else squat<float, float>(mode, n, phase, q, qd, warm, traj_out, u_out, qp_out);
 }
 }

@@ -158,3 +158,50 @@ def test_squat_jacobian_fp32_single_step(harness, oracle, omodel):
         worst = max(worst, rel_err(out["traj"][0], ref[k])); worst_u = max(worst_u, rel_err(out["u"][0], us[k]))
     assert worst < 1e-5, worst
     assert worst_u < 1e-4, worst_u
+
+
+# ----------------------------------------------------------------------------- OSC (StepOsc)
+def test_osc_fp64_matches_oracle_qp(harness, oracle, omodel):
+    """StepOsc: the device's reduced 14-variable box QP (osc_qp.cuh) reaches the optimum of the
+    reference's 39-variable / 45-row QP (oracle: dense active set on the QP exactly as assembled in
+    OSC_RBDL.cpp).  Parity on u, on the state, and on the QP's own optimality (status 0)."""
+    n = 400
+    ref, us, ops, acts, starts = run_facade(oracle, omodel, 3, lambda k, c: squat_osc_action(c.op_state(), k * 0.0005), n)
+    for k in range(0, n, 9):
+        q, v, ws = [x.copy() for x in starts[k]]
+        o = harness.ctrl_steps(3, q, v, ws, acts[k:k + 1])
+        assert rel_err(o["u"][0], us[k]) < 1e-7, k
+        assert rel_err(o["traj"][0], ref[k]) < 1e-9, k
+        assert o["qp"][0, 1] == 0 and o["qp"][0, 0] <= 30
+    q = QPOS_INIT_CTOR.copy(); qd = np.zeros(13); w = np.zeros(13)
+    traj, u = harness.squat(3, n, 0.0, q, qd, w)
+    assert rel_err(traj, ref) < 1e-8
+    assert rel_err(u, us) < 1e-6
+    # warm-started partition: one KKT solve per step in steady state
+    assert harness.last_qp[:, 1].max() == 0
+    assert np.median(harness.last_qp[:, 0]) == 1
+
+
+def test_osc_fp32_single_step(harness, oracle, omodel):
+    """fp32 physics + double-precision controller (the product's fp32 build), teacher-forced."""
+    n = 300
+    ref, us, ops, acts, starts = run_facade(oracle, omodel, 3, lambda k, c: squat_osc_action(c.op_state(), k * 0.0005), n)
+    worst = 0.0; worst_u = 0.0
+    for k in range(0, n, 5):
+        q, v, ws = [x.copy() for x in starts[k]]
+        o = harness.ctrl_steps(3, q, v, ws, acts[k:k + 1], f32=True)
+        worst = max(worst, rel_err(o["traj"][0], ref[k])); worst_u = max(worst_u, rel_err(o["u"][0], us[k]))
+    assert worst < 1e-5, worst
+    assert worst_u < 1e-3, worst_u
+
+
+def test_osc_actuator_limits_respected(harness, oracle, omodel):
+    """Aggressive targets drive u into the motor limits (OSC_RBDL.cpp:74-85 bounds); both solvers agree."""
+    c = oracle.Cassie2d(omodel)
+    a = np.array([50.0, 200.0, 0.0, 0.0, 0.0, 0.0, 30.0])
+    q, v = c.data.state(); ws = c.data.warmstart()
+    c.step_osc(a)
+    uo = c.last_ctrl()
+    o = harness.ctrl_steps(3, q.copy(), v.copy(), ws.copy(), a[None])
+    assert np.any(np.isclose(np.abs(uo), [12.2, 12.2, 0.9, 12.2, 12.2, 0.9]))
+    assert rel_err(o["u"][0], uo) < 1e-7

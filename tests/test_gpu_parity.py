@@ -167,6 +167,13 @@ def test_legacy_abi_matches_oracle_facade(LIB, oracle, omodel):
             act.left_force[i] = f[i]; act.right_force[i] = f[3 + i]
         L.StepJacobian(h, ct.byref(act)); c.step_jacobian(fo)
     check("jacobian", 1e-8)
+    L.Reset(h, ct.byref(cv.array_to_general_state(st))); c.reset(st)
+    for k in range(60):
+        L.GetOperationalSpaceState(h, ct.byref(xs))
+        a = squat_osc_action(cv.operational_state_to_array(xs), k * 0.0005)
+        ao = squat_osc_action(c.op_state(), k * 0.0005)
+        L.StepOsc(h, ct.byref(cv.array_to_operational_action(a))); c.step_osc(ao)
+    check("osc", 1e-8)
     L.Render(h)
 
 
@@ -183,21 +190,48 @@ def test_legacy_struct_untouched_slots(LIB):
 
 
 # ----------------------------------------------------------------------------- squatting loop
-@pytest.mark.parametrize("prec,tol", [(64, 1e-8), (32, 5e-3)])
-def test_squat_jacobian_kernel(E, LIB, oracle, omodel, prec, tol):
-    """config 1/3 squatting stream on device vs the oracle's closed loop, per-env phase offsets."""
+@pytest.mark.parametrize("mode,prec,tol", [(2, 64, 1e-8), (2, 32, 5e-3), (3, 64, 1e-8), (3, 32, 5e-3)])
+def test_squat_kernel(E, LIB, oracle, omodel, mode, prec, tol):
+    """config 1/3 squatting streams on device (standing_controller_jacobian -> StepJacobian, and
+    standing_controller_osc -> StepOsc with the QP in the loop) vs the oracle's closed loop, per-env
+    phase offsets.  fp64: 1e-8 after 400 closed-loop steps; fp32: stated tolerance 5e-3."""
     n, steps = 8, 400
     phase = 2 * np.pi * np.arange(n) / n
     b = E.Cassie2dBatch(n, precision=prec)
-    b.squat(LIB.MODE_JACOBIAN, steps, phase=torch.tensor(phase))
+    # two launches: the lagged op-space state, the clock and the QP partition persist across calls
+    b.squat(mode, steps // 2, phase=torch.tensor(phase))
+    b.squat(mode, steps - steps // 2, phase=torch.tensor(phase))
     got = b.get_general_state().cpu().numpy().astype(np.float64)
+    st = b.stats().cpu().numpy()
+    _, ref = oracle.rollout(omodel, n, steps, mode, phase=phase)
     for e in range(n):
-        c = oracle.Cassie2d(omodel)
-        t = 0.0
-        for k in range(steps):
-            c.step_jacobian(squat_jacobian_action(c.op_state(), t, phase[e]))
-            t = t + 0.0005
-        assert rel_err(got[e], c.general_state()) < tol, e
+        assert rel_err(got[e], ref[e]) < tol, e
+    if mode == 3:
+        assert (st[:, 3] == 0).all() and (st[:, 2] >= 1).all()   # QP optimal, >= 1 KKT solve
+    b.close()
+
+
+def test_osc_single_step_fp32_and_qp_status(E, LIB, oracle, omodel):
+    """StepOsc teacher-forced from oracle states: fp32 physics + double controller within 1e-5."""
+    n = 24
+    pres = []; refs = []; acts = []
+    c = oracle.Cassie2d(omodel)
+    for k in range(n * 12):
+        a = squat_osc_action(c.op_state(), k * 0.0005, 0.3)
+        if k % 12 == 5:
+            q, v = c.data.state()
+            pres.append((s26(oracle, q, v), c.data.warmstart())); acts.append(a)
+        c.step_osc(a)
+        if k % 12 == 5:
+            q, v = c.data.state(); refs.append(np.concatenate([q, v]))
+    b = E.Cassie2dBatch(n, precision=32)
+    b.reset(torch.tensor(np.array([p[0] for p in pres]), dtype=torch.float32, device=b.device))
+    b.set_warm_start(torch.tensor(np.array([p[1] for p in pres])))
+    b.step_osc(torch.tensor(np.array(acts)), 1)
+    q, v = q_from_s26(b.get_general_state().cpu().numpy().astype(np.float64))
+    assert rel_err(np.concatenate([q, v], axis=1), np.array(refs)) < 1e-5
+    st = b.stats().cpu().numpy()
+    assert (st[:, 3] == 0).all()
     b.close()
 
 
@@ -212,14 +246,15 @@ def py_stand_step(oracle, c, action, mode, n=10):
     return sp, r, bool(s[1] < 0.5)
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 3])
 def test_env_step_stand_fp64(E, LIB, oracle, omodel, mode):
-    n, T = 12, 60
+    """cassie_stand2d.py step(): Torque, PD and OSC (the published task) action spaces."""
+    n, T = (12, 60) if mode != 3 else (6, 40)
     rng = np.random.default_rng(21 + mode)
-    name = "Torque" if mode == 0 else "PD"
+    name = {0: "Torque", 1: "PD", 3: "OSC"}[mode]
     env = E.Cassie2dBatchEnv(n, task="stand", control_mode=name, precision=64, auto_reset=True)
     lo, hi = env.action_space
-    A = rng.uniform(lo, hi, (T, n, 6))
+    A = rng.uniform(lo, hi, (T, n, len(lo)))
     obs0 = env.reset().cpu().numpy()
     refs = [oracle.Cassie2d(omodel) for _ in range(n)]
     st = s26(oracle, QPOS_INIT_PY, np.zeros(13))
@@ -238,7 +273,7 @@ def test_env_step_stand_fp64(E, LIB, oracle, omodel, mode):
             assert bool(done[e]) == d, (k, e)
             if d:
                 c.reset(st); n_done += 1
-    assert n_done > 0   # the random policy does fall within the horizon: auto-reset is exercised
+    assert n_done > 0 or mode == 3   # random torque/PD policies fall within the horizon: auto-reset is exercised
     env.terminate()
 
 
