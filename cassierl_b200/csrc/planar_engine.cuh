@@ -29,6 +29,27 @@ extern bool cassie_force_general_path;
 
 namespace cassie {
 
+// sin and cos of a double argument of moderate size (joint angles, |a| < ~1e3): two-term Cody-Waite
+// reduction by pi/2 and the fdlibm __kernel_sin / __kernel_cos minimax polynomials on [-pi/4, pi/4]
+// (absolute error < 2e-16).  Used instead of the CUDA / libm sincos so that the host harness and
+// the device agree bit for bit and the kernel does not inline 20-odd copies of the slow-path range
+// reduction (13.7k of 44k SASS instructions before).
+CASSIE_HD void sincos_reduced(double a, double* sn, double* cs) {
+  const double k = rint(a * 6.36619772367581382433e-01);
+  double r = a - k * 1.57079632673412561417e+00;
+  r = r - k * 6.07710050650619224932e-11;
+  const double z = r * r;
+  const double ps = -1.66666666666666324348e-01 + z * (8.33333333332248946124e-03 + z * (-1.98412698298579493134e-04 +
+                    z * (2.75573137070700676789e-06 + z * (-2.50507602534068634195e-08 + z * 1.58969099521155010221e-10))));
+  const double pc = 4.16666666666666019037e-02 + z * (-1.38888888888741095749e-03 + z * (2.48015872894767294178e-05 +
+                    z * (-2.75573143513906633035e-07 + z * (2.08757232129817482790e-09 + z * -1.13596475577881948265e-11))));
+  const double s = r + r * z * ps;
+  const double c = 1.0 - 0.5 * z + z * z * pc;
+  const int q = ((int)k) & 3;
+  *sn = (q == 0) ? s : (q == 1) ? c : (q == 2) ? -s : -c;
+  *cs = (q == 0) ? c : (q == 1) ? -s : (q == 2) ? -c : s;
+}
+
 template <typename T> struct Num;
 template <> struct Num<float> {
   static CASSIE_HD void sincos_(float a, float* s, float* c) { sincosf(a, s, c); }
@@ -38,7 +59,7 @@ template <> struct Num<float> {
   static CASSIE_HD float exp_(float a) { return expf(a); }
 };
 template <> struct Num<double> {
-  static CASSIE_HD void sincos_(double a, double* s, double* c) { sincos(a, s, c); }
+  static CASSIE_HD void sincos_(double a, double* s, double* c) { sincos_reduced(a, s, c); }
   static CASSIE_HD double sqrt_(double a) { return sqrt(a); }
   static CASSIE_HD double abs_(double a) { return fabs(a); }
   static CASSIE_HD double pow_(double a, double b) { return pow(a, b); }
@@ -701,20 +722,21 @@ CASSIE_HD int constraint_solve_general(const PlanarModel<T>& m, Rows<T>& r, cons
 constexpr int kFastRows = 12;
 CASSIE_HD constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
-template <typename T>
+template <int NC, typename T>
 CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T LD[kNV][kNV], const T Dinv[kNV],
                                     const T qs[kNV], const T warm[kNV], T fc[kNV]) {
+  constexpr int NR = 4 + 2 * NC;  // rows handled by this instantiation (NC contact pairs)
   const int n = r.n;
-  for (int i = n; i < kFastRows; i++) {  // inert padding
+  for (int i = n; i < NR; i++) {  // inert padding
     CASSIE_UNROLL
     for (int c = 0; c < 8; c++) r.J[i][c] = T(0);
     r.leg[i] = 0;
     r.R[i] = T(1);
     r.b[i] = T(0);
   }
-  T A[kFastRows * (kFastRows + 1) / 2], b[kFastRows], f[kFastRows], jar[kFastRows];
+  T A[NR * (NR + 1) / 2], b[NR], f[NR], jar[NR];
   CASSIE_UNROLL
-  for (int i = 0; i < kFastRows; i++) {
+  for (int i = 0; i < NR; i++) {
     T Bi[kNV];
     expand_row(r.J[i], r.leg[i], Bi);
     const T maref = r.b[i];
@@ -722,7 +744,7 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
     jar[i] = maref + dot8_dense(r.J[i], r.leg[i], warm);
     if (i < 4 || i < n) solve(LD, Dinv, Bi);
     CASSIE_UNROLL
-    for (int j = 0; j < kFastRows; j++)
+    for (int j = 0; j < NR; j++)
       if (j <= i) A[tri(i, j)] = dot8_dense(r.J[j], r.leg[j], Bi);
     A[tri(i, i)] += r.R[i];
   }
@@ -732,7 +754,7 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
   {
     const T mu = m.con_mu / Num<T>::sqrt_(m.impratio);
     CASSIE_UNROLL
-    for (int i = 4; i < kFastRows; i += 2) {
+    for (int i = 4; i < NR; i += 2) {
       const T N = jar[i] * mu, U1 = jar[i + 1] * m.con_mu, Tn = Num<T>::abs_(U1);
       const T D0 = T(1) / r.R[i], D1 = T(1) / r.R[i + 1];
       T f0, f1;
@@ -750,20 +772,20 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
   {
     T cost = T(0);
     CASSIE_UNROLL
-    for (int i = 0; i < kFastRows; i++) {
+    for (int i = 0; i < NR; i++) {
       T s = T(0);
       CASSIE_UNROLL
-      for (int c = 0; c < kFastRows; c++) s += A[tri(i, c)] * f[c];
+      for (int c = 0; c < NR; c++) s += A[tri(i, c)] * f[c];
       cost += f[i] * (T(0.5) * s + b[i]);
     }
     if (cost > T(0)) {
       CASSIE_UNROLL
-      for (int i = 0; i < kFastRows; i++) f[i] = T(0);
+      for (int i = 0; i < NR; i++) f[i] = T(0);
     }
   }
-  T inv[kFastRows];
+  T inv[NR];
   CASSIE_UNROLL
-  for (int i = 0; i < kFastRows; i++) inv[i] = T(1) / A[tri(i, i)];
+  for (int i = 0; i < NR; i++) inv[i] = T(1) / A[tri(i, i)];
   const T scale = T(1) / (m.meaninertia * T(kNV));
   const T inv_mu = T(1) / m.con_mu;
   int iter = 0;
@@ -773,7 +795,7 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
     for (int i = 0; i < 4; i++) {  // equality rows: unbounded
       T res = b[i];
       CASSIE_UNROLL
-      for (int c = 0; c < kFastRows; c++) res += A[tri(i, c)] * f[c];
+      for (int c = 0; c < NR; c++) res += A[tri(i, c)] * f[c];
       const T fn = f[i] - res * inv[i];
       const T d = fn - f[i];
       const T change = T(0.5) * d * d * A[tri(i, i)] + d * res;
@@ -782,10 +804,10 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
       improvement -= keep ? change : T(0);
     }
     CASSIE_UNROLL
-    for (int i = 4; i < kFastRows; i += 2) {  // elliptic contact: normal + one tangent
+    for (int i = 4; i < NR; i += 2) {  // elliptic contact: normal + one tangent
       T res0 = b[i], res1 = b[i + 1];
       CASSIE_UNROLL
-      for (int c = 0; c < kFastRows; c++) { res0 += A[tri(i, c)] * f[c]; res1 += A[tri(i + 1, c)] * f[c]; }
+      for (int c = 0; c < NR; c++) { res0 += A[tri(i, c)] * f[c]; res1 += A[tri(i + 1, c)] * f[c]; }
       const T old0 = f[i], old1 = f[i + 1];
       const T A00 = A[tri(i, i)], A01 = A[tri(i + 1, i)], A11 = A[tri(i + 1, i + 1)];
       // (a) normal / ray update
@@ -816,7 +838,7 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
   CASSIE_UNROLL
   for (int i = 0; i < kNV; i++) fc[i] = T(0);
   CASSIE_UNROLL
-  for (int i = 0; i < kFastRows; i++) {
+  for (int i = 0; i < NR; i++) {
     const T fi = f[i];
     const int leg = r.leg[i];
     fc[0] += r.J[i][0] * fi; fc[1] += r.J[i][1] * fi; fc[2] += r.J[i][2] * fi;
@@ -885,7 +907,8 @@ CASSIE_HD void physics_step(const PlanarModel<T>& m, const PlanarModel<TG>& mg, 
 #else
   const bool fast_ok = true;
 #endif
-  if (fast_ok && nlimit == 0 && n <= kFastRows) sweeps = constraint_solve_fast(m, r, LD, Dinv, qs, warm, fc);
+  if (fast_ok && nlimit == 0 && n <= 8) sweeps = constraint_solve_fast<2>(m, r, LD, Dinv, qs, warm, fc);
+  else if (fast_ok && nlimit == 0 && n <= kFastRows) sweeps = constraint_solve_fast<4>(m, r, LD, Dinv, qs, warm, fc);
   else sweeps = constraint_solve_general(m, r, LD, Dinv, qs, warm, fc);
   // qacc = qacc_smooth + M^-1 qfrc_constraint
   T dq[kNV];

@@ -128,7 +128,26 @@ int orc_qp_solve(int n, int mc, const double* G, const double* g, const double* 
       for (int j = 0; j < n; j++) { K[(n + w) * N + j] = ca[W[w] * n + j]; K[j * N + n + w] = ca[W[w] * n + j]; }
       rhs[n + w] = 0;
     }
-    if (gauss_solve(N, K, rhs)) { rc = -2; break; }
+    int singular = gauss_solve(N, K, rhs);
+    for (int attempt = 0; singular && attempt < 2; attempt++) {
+      /* singular KKT = linearly dependent working set (e.g. beta_x <= mu beta_z, beta_z >= 0 and
+       * beta_x >= 0 all active at the apex of a friction pyramid): re-solve with a tiny dual
+       * regularisation, which splits the multipliers among the dependent rows */
+      const double eps = attempt == 0 ? 1e-10 : 1e-7;
+      for (int i = 0; i < N * N; i++) K[i] = 0;
+      for (int i = 0; i < n; i++) {
+        double s = g[i];
+        for (int j = 0; j < n; j++) { K[i * N + j] = G[i * n + j]; s += G[i * n + j] * x[j]; }
+        rhs[i] = -s;
+      }
+      for (int w = 0; w < nw; w++) {
+        for (int j = 0; j < n; j++) { K[(n + w) * N + j] = ca[W[w] * n + j]; K[j * N + n + w] = ca[W[w] * n + j]; }
+        K[(n + w) * N + n + w] = -eps;
+        rhs[n + w] = 0;
+      }
+      singular = gauss_solve(N, K, rhs);
+    }
+    if (singular) { rc = -2; break; }
     double pn = 0, xn = 1;
     for (int i = 0; i < n; i++) { pn = fmax(pn, fabs(rhs[i])); xn = fmax(xn, fabs(x[i])); }
     if (pn <= 1e-12 * xn) {
@@ -145,9 +164,9 @@ int orc_qp_solve(int n, int mc, const double* G, const double* g, const double* 
       int inW = 0;
       for (int w = 0; w < nw; w++) if (W[w] == k2) inW = 1;
       if (inW) continue;
-      double ap = 0, ax = 0;
-      for (int j = 0; j < n; j++) { ap += ca[k2 * n + j] * rhs[j]; ax += ca[k2 * n + j] * x[j]; }
-      if (ap > 1e-13) {
+      double ap = 0, ax = 0, an = 0;
+      for (int j = 0; j < n; j++) { ap += ca[k2 * n + j] * rhs[j]; ax += ca[k2 * n + j] * x[j]; an = fmax(an, fabs(ca[k2 * n + j])); }
+      if (ap > 1e-13 && ap > 1e-11 * pn * an) { /* rounding noise of a large step must not look like motion */
         double a = (cb[k2] - ax) / ap;
         if (a < 0) a = 0;
         if (a < alpha) { alpha = a; block = k2; }

@@ -205,3 +205,16 @@ def test_osc_actuator_limits_respected(harness, oracle, omodel):
     o = harness.ctrl_steps(3, q.copy(), v.copy(), ws.copy(), a[None])
     assert np.any(np.isclose(np.abs(uo), [12.2, 12.2, 0.9, 12.2, 12.2, 0.9]))
     assert rel_err(o["u"][0], uo) < 1e-7
+
+
+def test_osc_phases_match_oracle_rollout(harness, oracle, omodel):
+    """The bench stream (per-env phase offsets) through orc_rollout, including the regime where the
+    commanded descent unloads the feet and the QP sits at the apex of the friction pyramids."""
+    n, steps = 8, 300
+    phase = 2 * np.pi * np.arange(n) / n
+    _, ref = oracle.rollout(omodel, n, steps, 3, phase=phase)
+    for e in range(n):
+        q = QPOS_INIT_CTOR.copy(); qd = np.zeros(13); w = np.zeros(13)
+        harness.squat(3, steps, phase[e], q, qd, w)
+        assert rel_err(oracle.state26_from_qpos_qvel(q, qd), ref[e]) < 1e-4, e
+        assert harness.last_qp[:, 1].max() == 0
