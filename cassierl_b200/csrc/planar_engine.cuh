@@ -907,8 +907,16 @@ CASSIE_HD void physics_step(const PlanarModel<T>& m, const PlanarModel<TG>& mg, 
 #else
   const bool fast_ok = true;
 #endif
-  if (fast_ok && nlimit == 0 && n <= 8) sweeps = constraint_solve_fast<2>(m, r, LD, Dinv, qs, warm, fc);
-  else if (fast_ok && nlimit == 0 && n <= kFastRows) sweeps = constraint_solve_fast<4>(m, r, LD, Dinv, qs, warm, fc);
+  if (fast_ok && nlimit == 0 && n <= kFastRows) {
+    // 8-row (two contacts) or 12-row variant, chosen per WARP so that lanes never run both
+#ifdef __CUDA_ARCH__
+    const bool wide = __any_sync(__activemask(), n > 8);
+#else
+    const bool wide = n > 8;
+#endif
+    if (wide) sweeps = constraint_solve_fast<4>(m, r, LD, Dinv, qs, warm, fc);
+    else sweeps = constraint_solve_fast<2>(m, r, LD, Dinv, qs, warm, fc);
+  }
   else sweeps = constraint_solve_general(m, r, LD, Dinv, qs, warm, fc);
   // qacc = qacc_smooth + M^-1 qfrc_constraint
   T dq[kNV];
