@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "lib", "libcassie2d.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr"]
-UNITS = ["kernels_f32.cu", "kernels_f64.cu", "cassie2d_api.cu", "mjcf_flatten.cpp"]
+UNITS = ["kernels_f32.cu", "kernels_f64.cu", "rollout_f32.cu", "rollout_f64.cu", "cassie2d_api.cu", "mjcf_flatten.cpp"]
 
 
 def _deps():

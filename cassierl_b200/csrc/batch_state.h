@@ -30,6 +30,8 @@ struct BatchView {
   T* jsum0;         // [n]      frozen qstate joint sum of the imitation reward (App. D.4)
   uint32_t* qp_set; // [n]      OSC QP partition (free / at-lower / at-upper) carried across steps, like
                     //          the qpOASES hot start that survives resets in the reference (App. D.3)
+  int32_t* ep_len;      // [n]  policy steps since the last reset (max_path_length bookkeeping of the sampler)
+  int32_t* policy_step; // [n]  policy steps since init: the Philox counter of the action noise
   int32_t* stats;   // [n][4]   rows, PGS sweeps, QP iterations, QP status of the last substep
   const double* traj;  // [traj_rows][13] reference qpos (device), may be null
   int traj_rows;
@@ -70,6 +72,10 @@ struct Launch {
   static cudaError_t env_reset(const ModelPair<T>& mp, const BatchView<T>& v, int task, int flags, const T* state26,
                                T* obs, cudaStream_t s);
 };
+
+struct RolloutArgs;
+template <typename T>
+cudaError_t launch_rollout(const ModelPair<T>& mp, const BatchView<T>& v, const RolloutArgs& a, cudaStream_t s);
 
 long long kernel_launch_count();
 void count_launch();

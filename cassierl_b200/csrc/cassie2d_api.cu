@@ -11,6 +11,7 @@
 
 #include "../../include/cassie2d.h"
 #include "batch_state.h"
+#include "rollout_args.h"
 #include "mjcf_flatten.h"
 
 namespace cassie {
@@ -93,6 +94,8 @@ static int alloc_view(CassieBatch* h, BatchView<T>& v) {
   CU_OK(A((void**)&v.jsum0, sizeof(T) * n));
   CU_OK(A((void**)&v.stats, sizeof(int32_t) * 4 * n));
   CU_OK(A((void**)&v.qp_set, sizeof(uint32_t) * n));
+  CU_OK(A((void**)&v.ep_len, sizeof(int32_t) * n));
+  CU_OK(A((void**)&v.policy_step, sizeof(int32_t) * n));
   v.traj = nullptr; v.traj_rows = 0; v.traj_tmax = 1.0;
   CU_OK(A(&h->scratch_state, sizeof(T) * 26));
   CU_OK(A(&h->d_action, sizeof(T) * 7 * n));
@@ -274,6 +277,44 @@ int Cassie2dBatchSetTrajectory(CassieBatch* h, const double* qpos_rows_host, int
   h->v32.traj = h->v64.traj = h->d_traj;
   h->v32.traj_rows = h->v64.traj_rows = n_rows;
   h->v32.traj_tmax = h->v64.traj_tmax = t_max;
+  return 0;
+}
+
+// action-space boxes of the reference envs (cassie_stand2d.py:255-268 == cassie2d.py:353-368)
+static void action_box(int mode, double lo[7], double hi[7]) {
+  const double d2r = 3.14159265358979323846 / 180.0;
+  for (int i = 0; i < 7; i++) { lo[i] = 0; hi[i] = 0; }
+  if (mode == 3) {
+    const double l[7] = {-2e1, -2e1, -2e1, 0, -2e1, 0, -2e1};
+    for (int i = 0; i < 7; i++) { lo[i] = l[i]; hi[i] = 2e1; }
+  } else if (mode == 0) {
+    const double t[6] = {12.0, 12.0, 0.9, 12.0, 12.0, 0.9};
+    for (int i = 0; i < 6; i++) { lo[i] = -t[i]; hi[i] = t[i]; }
+  } else {
+    const double h6[6] = {80.0, -37.0, -30.0, 80.0, -37.0, -30.0}, l6[6] = {-50.0, -164.0, -140.0, -50.0, -164.0, -140.0};
+    for (int i = 0; i < 6; i++) { lo[i] = l6[i] * d2r; hi[i] = h6[i] * d2r; }
+  }
+}
+
+int Cassie2dBatchRollout(CassieBatch* h, int task, int mode, const void* params_dev, int n_params, int n_policy_steps,
+                         int n_substeps, int max_path_length, int flags, int normalize, unsigned long long seed,
+                         unsigned int first_global_env, void* obs_dev, void* action_dev, void* mean_dev, void* reward_dev,
+                         uint8_t* done_dev, void* stream) {
+  if (!h || !params_dev || !obs_dev || !action_dev || !mean_dev || !reward_dev || !done_dev) return fail("null argument");
+  if (task != 0 && task != 1) return fail("bad task");
+  if (mode != 0 && mode != 1 && mode != 3) return fail("bad mode (the Python envs offer Torque, PD, OSC)");
+  if (n_policy_steps < 0 || n_substeps < 0 || max_path_length <= 0) return fail("bad step counts");
+  if (task == 1 && !h->d_traj) return fail("imitation task needs Cassie2dBatchSetTrajectory first");
+  const int odim = task == 1 ? 26 : 17, adim = mode == 3 ? 7 : 6;
+  const int want = odim * 32 + 32 + 32 * 32 + 32 + 32 * adim + adim + adim;
+  if (n_params != want) return fail("policy parameter vector has " + std::to_string(n_params) + " entries, expected " + std::to_string(want));
+  if (set_device(h)) return -1;
+  RolloutArgs a;
+  a.task = task; a.mode = mode; a.n_substeps = n_substeps; a.T_steps = n_policy_steps; a.max_path_length = max_path_length;
+  a.flags = flags; a.normalize = normalize; a.seed = seed; a.env0 = first_global_env;
+  a.params = params_dev; a.obs = obs_dev; a.act = action_dev; a.mean = mean_dev; a.rew = reward_dev; a.done = done_dev;
+  action_box(mode, a.act_lo, a.act_hi);
+  DISPATCH(h, CU_OK(launch_rollout<R>(MP<R>(h), BV<R>(h), a, (cudaStream_t)stream)));
   return 0;
 }
 

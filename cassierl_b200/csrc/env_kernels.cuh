@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(128) k_env_reset(const __grid_constant__ Model
 #pragma unroll
   for (int i = 0; i < kNV; i++) { v.qpos[(size_t)i * n + e] = q[i]; v.qvel[(size_t)i * n + e] = qd[i]; }
   v.clock[e] = 0.0;
+  v.ep_len[e] = 0;
   v.jsum0[e] = q[3] + q[4] + q[6] + q[8] + q[9] + q[11];
   if (obs) {
     T o18[18], ref9[9];

@@ -789,48 +789,71 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
   const T scale = T(1) / (m.meaninertia * T(kNV));
   const T inv_mu = T(1) / m.con_mu;
   int iter = 0;
+  // Latency-oriented sweep: everything that only depends on the forces of the PREVIOUS sweep (the
+  // upper-triangle part of each residual, the ray-update denominators) is computed up front with full
+  // ILP; the Gauss-Seidel chain through the freshly updated forces is one FMA + one add per row plus
+  // the projection.  The per-block "cost went up -> revert" test of mj_solPGS is dropped here: every
+  // block update is an exact minimisation of a convex sub-problem, so the change is <= 0 in exact
+  // arithmetic and the test can only fire on rounding noise (the general path keeps it).
   while (iter < m.iterations) {
+    T hi[NR];  // b_i + sum_{c >= i} A_ic f_c  (forces of the previous sweep)
+    CASSIE_UNROLL
+    for (int i = 0; i < NR; i++) {
+      T sacc = b[i];
+      CASSIE_UNROLL
+      for (int c = 0; c < NR; c++)
+        if (c >= i) sacc += A[tri(i, c)] * f[c];
+      hi[i] = sacc;
+    }
+    T rden[NC > 0 ? NC : 1];
+    CASSIE_UNROLL
+    for (int p = 0; p < NC; p++) {
+      const int i = 4 + 2 * p;
+      const T o0 = f[i], o1 = f[i + 1];
+      const T denom = o0 * (A[tri(i, i)] * o0 + A[tri(i + 1, i)] * o1) + o1 * (A[tri(i + 1, i)] * o0 + A[tri(i + 1, i + 1)] * o1);
+      rden[p] = denom >= T(kMinVal) ? T(1) / denom : T(0);
+    }
     T improvement = T(0);
     CASSIE_UNROLL
     for (int i = 0; i < 4; i++) {  // equality rows: unbounded
-      T res = b[i];
+      T lo = T(0);
       CASSIE_UNROLL
-      for (int c = 0; c < NR; c++) res += A[tri(i, c)] * f[c];
-      const T fn = f[i] - res * inv[i];
-      const T d = fn - f[i];
-      const T change = T(0.5) * d * d * A[tri(i, i)] + d * res;
-      const bool keep = !(change > T(1e-10));
-      f[i] = keep ? fn : f[i];
-      improvement -= keep ? change : T(0);
+      for (int c = 0; c < NR; c++)
+        if (c < i) lo += A[tri(i, c)] * f[c];
+      const T res = hi[i] + lo;
+      const T d = -res * inv[i];
+      f[i] += d;
+      improvement -= T(0.5) * d * d * A[tri(i, i)] + d * res;
     }
     CASSIE_UNROLL
-    for (int i = 4; i < NR; i += 2) {  // elliptic contact: normal + one tangent
-      T res0 = b[i], res1 = b[i + 1];
+    for (int p = 0; p < NC; p++) {  // elliptic contact: normal + one tangent
+      const int i = 4 + 2 * p;
+      T lo0 = T(0), lo1 = T(0);
       CASSIE_UNROLL
-      for (int c = 0; c < NR; c++) { res0 += A[tri(i, c)] * f[c]; res1 += A[tri(i + 1, c)] * f[c]; }
+      for (int c = 0; c < NR; c++)
+        if (c < i) { lo0 += A[tri(i, c)] * f[c]; lo1 += A[tri(i + 1, c)] * f[c]; }
       const T old0 = f[i], old1 = f[i + 1];
       const T A00 = A[tri(i, i)], A01 = A[tri(i + 1, i)], A11 = A[tri(i + 1, i + 1)];
+      const T res0 = hi[i] + lo0;
+      // row i+1's "hi" sum starts at c = i+1; add the c = i term (old force) to complete the residual
+      const T res1 = hi[i + 1] + A01 * old0 + lo1;
       // (a) normal / ray update
-      const T fa = old0 - res0 * inv[i];
-      const T denom = old0 * (A00 * old0 + A01 * old1) + old1 * (A01 * old0 + A11 * old1);
-      T x = -(old0 * res0 + old1 * res1) / (denom >= T(kMinVal) ? denom : T(1));
-      x = denom >= T(kMinVal) ? x : T(0);
-      x = (old0 + x * old0 < T(0)) ? T(-1) : x;
-      const bool low = old0 < T(kMinVal);
-      T f0 = low ? (fa < T(0) ? T(0) : fa) : old0 + x * old0;
+      T fa = old0 - res0 * inv[i];
+      fa = fa < T(0) ? T(0) : fa;
+      T x = -(old0 * res0 + old1 * res1) * rden[p];
+      x = x < T(-1) ? T(-1) : x;
+      const T f0 = old0 < T(kMinVal) ? fa : old0 + x * old0;
       // (b) friction update with the normal force fixed (mju_QCQP2 collapses to a clamp)
-      const T bc = res1 - A11 * old1 + A01 * (f0 - old0);
+      const T bc = (res1 - A11 * old1 - A01 * old0) + A01 * f0;
       T v = -bc * inv[i + 1];
       const T vs = v * inv_mu;
       const T lim = m.con_mu * f0;
       v = (vs * vs - f0 * f0 >= T(1e-10)) ? (v > T(0) ? lim : -lim) : v;
-      T f1 = f0 < T(kMinVal) ? T(0) : v;
+      const T f1 = f0 < T(kMinVal) ? T(0) : v;
       const T d0 = f0 - old0, d1 = f1 - old1;
-      const T change = T(0.5) * (d0 * (A00 * d0 + A01 * d1) + d1 * (A01 * d0 + A11 * d1)) + d0 * res0 + d1 * res1;
-      const bool keep = !(change > T(1e-10));
-      f[i] = keep ? f0 : old0;
-      f[i + 1] = keep ? f1 : old1;
-      improvement -= keep ? change : T(0);
+      improvement -= T(0.5) * (d0 * (A00 * d0 + A01 * d1) + d1 * (A01 * d0 + A11 * d1)) + d0 * res0 + d1 * res1;
+      f[i] = f0;
+      f[i + 1] = f1;
     }
     iter++;
     if (improvement * scale < m.tolerance) break;

@@ -1,0 +1,5 @@
+// fp32 instantiation of the fused rollout kernel (policy MLP + env step), see rollout_kernels.cuh
+#include "rollout_kernels.cuh"
+namespace cassie {
+template cudaError_t launch_rollout<float>(const ModelPair<float>&, const BatchView<float>&, const RolloutArgs&, cudaStream_t);
+}

@@ -1,0 +1,5 @@
+// fp64 instantiation of the fused rollout kernel (parity build), see rollout_kernels.cuh
+#include "rollout_kernels.cuh"
+namespace cassie {
+template cudaError_t launch_rollout<double>(const ModelPair<double>&, const BatchView<double>&, const RolloutArgs&, cudaStream_t);
+}

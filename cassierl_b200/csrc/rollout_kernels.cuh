@@ -1,0 +1,218 @@
+// Rollout collection fused into one kernel (BASELINE configs[4]): what rllab's
+// BatchSampler does around the reference env, one Python call and twelve FFI calls per policy step
+// (rllab/envs/trpo_cassie.py:13-55 -> rollout() -> GaussianMLPPolicy.get_action -> NormalizedEnv.step
+// -> Cassie2dEnv.step), here T policy steps per launch for every env:
+//   obs -> tanh MLP (26|17 -> 32 -> 32 -> adim) -> a = mean + exp(log_std) * eps -> NormalizedEnv affine
+//   map + clip -> n_substeps x Step* -> obs / reward / done -> auto-reset at done or max_path_length.
+// The policy is 2.0 k MAC per policy step against ~0.5 MFLOP for the ten simulator steps it drives
+// (0.4 %), so it runs as per-thread FP32 FMAs with the weights broadcast from shared memory; a
+// tensor-core tile for a [N x 32] x [32 x 32] product would be launch- and fill-latency bound
+// (DESIGN.md section 9).  eps comes from Philox4x32-10 keyed by (seed, global env id, policy step), so
+// results do not depend on the launch partition or the GPU count.
+#pragma once
+#include "env_kernels.cuh"
+#include "rollout_args.h"
+
+namespace cassie {
+
+constexpr int kHidden = 32;  // hidden_sizes=(32, 32), trpo_cassie.py:24
+
+// ---- Philox4x32-10 (Salmon et al., SC'11), counter-based
+__host__ __device__ inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  for (int r = 0; r < 10; r++) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+// eight standard normals for (seed, env, step): two Philox blocks, Box-Muller on (0,1] uniforms
+template <typename T>
+__device__ inline void normal8(uint64_t seed, uint32_t env, uint32_t step, T out[8]) {
+#pragma unroll
+  for (int b = 0; b < 2; b++) {
+    uint32_t c[4] = {env, step, (uint32_t)b, 0u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      const float u1 = ((float)(c[2 * p] >> 8) + 1.0f) * (1.0f / 16777216.0f);   // (0, 1]
+      const float u2 = (float)(c[2 * p + 1] >> 8) * (1.0f / 16777216.0f);        // [0, 1)
+      const float rad = sqrtf(-2.0f * logf(u1));
+      float sn, cs;
+      sincospif(2.0f * u2, &sn, &cs);
+      out[4 * b + 2 * p] = (T)(rad * cs);
+      out[4 * b + 2 * p + 1] = (T)(rad * sn);
+    }
+  }
+}
+
+template <typename T>
+struct RolloutDev {
+  int task, flags, n_sub, T_steps, max_path_length, normalize;
+  uint64_t seed;
+  uint32_t env0;       // global id of this batch's env 0
+  const T* params;     // flat [W1(in x 32) | b1 | W2(32 x 32) | b2 | W3(32 x adim) | b3 | log_std(adim)]  (Lasagne order)
+  T* obs;              // [T][n][odim]
+  T* act;              // [T][n][adim]  raw policy actions (what rllab stores in paths)
+  T* mean;             // [T][n][adim]  agent_infos["mean"]
+  T* rew;              // [T][n]
+  uint8_t* done;       // [T][n]  1 = env terminated, 2 = max_path_length reached
+  T act_lo[7], act_hi[7];
+  T reset_state[26];
+};
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kBlock) k_rollout(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v,
+                                                     const __grid_constant__ RolloutDev<T> a) {
+  constexpr int adim = action_dim(MODE);
+  const int odim = a.task == kTaskStand ? 17 : 26;
+  extern __shared__ unsigned char smem_raw[];
+  T* sp = reinterpret_cast<T*>(smem_raw);
+  const int n_params = odim * kHidden + kHidden + kHidden * kHidden + kHidden + kHidden * adim + adim + adim;
+  for (int i = threadIdx.x; i < n_params; i += kBlock) sp[i] = a.params[i];
+  T* sobs = sp + n_params;  // [26][kBlock] per-thread observation staging
+  __syncthreads();
+  const T* W1 = sp; const T* b1 = W1 + odim * kHidden; const T* W2 = b1 + kHidden; const T* b2 = W2 + kHidden * kHidden;
+  const T* W3 = b2 + kHidden; const T* b3 = W3 + kHidden * adim; const T* lstd = b3 + adim;
+
+  const int e = blockIdx.x * kBlock + threadIdx.x;
+  if (e >= v.n) return;
+  T q[kNV], qd[kNV], w[kNV], u[kNU];
+  load_env(v, e, q, qd, w);
+  Rows<T> rows;
+  OpState<T> op;
+  load_op(v, e, op);
+  StepStats st = {0, 0, 0u};
+  OscStats qs = {0, 0};
+  double t = v.clock[e];
+  unsigned qps = v.qp_set[e];
+  int ep_len = v.ep_len[e];
+  uint32_t pstep = (uint32_t)v.policy_step[e];
+  const size_t n = (size_t)v.n;
+
+  for (int k = 0; k < a.T_steps; k++) {
+    // ---- observation of the current state (what the previous step / reset returned)
+    T o18[18], ref9[9];
+    op_state_array(op, q, qd, o18);
+    write_obs(v, a.task, e, o18, t, a.obs + (size_t)k * n * odim, ref9);
+    {
+      T o[17];
+      pos_invariant_obs(o18, o);
+#pragma unroll
+      for (int i = 0; i < 17; i++) sobs[i * kBlock + threadIdx.x] = o[i];
+      if (a.task != kTaskStand) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) sobs[(17 + i) * kBlock + threadIdx.x] = ref9[i];
+      }
+    }
+    // ---- GaussianMLPPolicy forward: tanh hidden layers, linear mean head (trpo_cassie.py:21-27)
+    T h1[kHidden], h2[kHidden], mu[adim], act[7];
+#pragma unroll
+    for (int j = 0; j < kHidden; j++) h1[j] = b1[j];
+    for (int i = 0; i < odim; i++) {
+      const T x = sobs[i * kBlock + threadIdx.x];
+#pragma unroll
+      for (int j = 0; j < kHidden; j++) h1[j] += x * W1[i * kHidden + j];
+    }
+#pragma unroll
+    for (int j = 0; j < kHidden; j++) { h1[j] = tanh(h1[j]); h2[j] = b2[j]; }
+#pragma unroll
+    for (int i = 0; i < kHidden; i++) {
+#pragma unroll
+      for (int j = 0; j < kHidden; j++) h2[j] += h1[i] * W2[i * kHidden + j];
+    }
+#pragma unroll
+    for (int j = 0; j < kHidden; j++) h2[j] = tanh(h2[j]);
+#pragma unroll
+    for (int c = 0; c < adim; c++) {
+      T s = b3[c];
+#pragma unroll
+      for (int i = 0; i < kHidden; i++) s += h2[i] * W3[i * adim + c];
+      mu[c] = s;
+    }
+    // ---- a = mean + exp(log_std) * eps ; NormalizedEnv: lb + (a + 1) / 2 (ub - lb), clipped (trpo_cassie.py:13)
+    T eps[8];
+    normal8(a.seed, a.env0 + (uint32_t)e, pstep, eps);
+#pragma unroll
+    for (int c = 0; c < adim; c++) {
+      const T raw = mu[c] + exp(lstd[c]) * eps[c];
+      a.act[((size_t)k * n + e) * adim + c] = raw;
+      a.mean[((size_t)k * n + e) * adim + c] = mu[c];
+      T x = raw;
+      if (a.normalize) x = a.act_lo[c] + (raw + T(1)) * T(0.5) * (a.act_hi[c] - a.act_lo[c]);
+      act[c] = x < a.act_lo[c] ? a.act_lo[c] : (x > a.act_hi[c] ? a.act_hi[c] : x);
+    }
+    // ---- Cassie2dEnv.step(action, n)
+    for (int s = 0; s < a.n_sub; s++) {
+      controller_step<MODE>(mp.phys, mp.phys_d, ctrl_model<MODE>(mp), q, qd, w, act, rows, u, s == a.n_sub - 1 ? &op : nullptr, &st, &qs, &qps);
+      t += 0.0005;
+    }
+    T r;
+    int done;
+    op_state_array(op, q, qd, o18);
+    if (a.task == kTaskStand) {
+      T o[17];
+      pos_invariant_obs(o18, o);
+      stand_reward(o18, o, act, adim, r, done);
+    } else {
+      const int idx9[9] = {0, 1, 2, 3, 4, 6, 8, 9, 11};
+      const int row = v.traj ? traj_index(t, v.traj_tmax, v.traj_rows) : 0;
+#pragma unroll
+      for (int i = 0; i < 9; i++) ref9[i] = v.traj ? (T)v.traj[(size_t)row * 13 + idx9[i]] : T(0);
+      const T jsum = (a.flags & 4) ? q[3] + q[4] + q[6] + q[8] + q[9] + q[11] : v.jsum0[e];
+      imitate_reward(o18, ref9, jsum, r, done);
+    }
+    ep_len++;
+    pstep++;
+    int flag = done ? 1 : (ep_len >= a.max_path_length ? 2 : 0);
+    a.rew[(size_t)k * n + e] = r;
+    a.done[(size_t)k * n + e] = (uint8_t)flag;
+    if (flag) {  // rollout(): the path ends, the sampler calls env.reset()
+      state26_to_q(a.reset_state, q, qd);
+      t = 0.0;
+      ep_len = 0;
+      v.jsum0[e] = q[3] + q[4] + q[6] + q[8] + q[9] + q[11];
+      if (a.flags & 2) {
+        Kin<T> kc;
+        forward_kinematics(mp.ctrl, q, qd, kc);
+        op_state_from_kin(mp.ctrl, kc, q, op);
+      }
+    }
+  }
+  v.clock[e] = t;
+  v.qp_set[e] = qps;
+  v.ep_len[e] = ep_len;
+  v.policy_step[e] = (int32_t)pstep;
+  store_env(v, e, q, qd, w);
+  store_op(v, e, op);
+  store_stats(v.stats, v.n, e, st, qs);
+}
+
+
+template <typename T>
+cudaError_t launch_rollout(const ModelPair<T>& mp, const BatchView<T>& v, const RolloutArgs& a, cudaStream_t s) {
+  RolloutDev<T> d;
+  d.task = a.task; d.flags = a.flags; d.n_sub = a.n_substeps; d.T_steps = a.T_steps; d.max_path_length = a.max_path_length;
+  d.normalize = a.normalize; d.seed = a.seed; d.env0 = a.env0;
+  d.params = (const T*)a.params; d.obs = (T*)a.obs; d.act = (T*)a.act; d.mean = (T*)a.mean; d.rew = (T*)a.rew; d.done = a.done;
+  for (int i = 0; i < 7; i++) { d.act_lo[i] = (T)a.act_lo[i]; d.act_hi[i] = (T)a.act_hi[i]; }
+  const double qi[26] = {0.0, 0.939, 0.0, 0.0, 0.0, 0.0, 0.68111815, -1.40730357, 1.62972042, -1.77611107, -0.61968407,
+                         0.0, 0.0, 0.0, 0.0, 0.0, 0.68111815, -1.40730357, 1.62972042, -1.77611107, -0.61968407,
+                         0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int i = 0; i < 26; i++) d.reset_state[i] = (T)qi[i];
+  const int odim = a.task == kTaskStand ? 17 : 26, adim = action_dim(a.mode);
+  const int n_params = odim * kHidden + kHidden + kHidden * kHidden + kHidden + kHidden * adim + adim + adim;
+  const size_t smem = sizeof(T) * (size_t)(n_params + 26 * kBlock);
+  const unsigned g = grid_for(v.n, kBlock);
+  switch (a.mode) {
+    case kModeTorque: k_rollout<T, kModeTorque><<<g, kBlock, smem, s>>>(mp, v, d); break;
+    case kModePd: k_rollout<T, kModePd><<<g, kBlock, smem, s>>>(mp, v, d); break;
+    case kModeOsc: k_rollout<T, kModeOsc><<<g, kBlock, smem, s>>>(mp, v, d); break;
+    default: return cudaErrorInvalidValue;
+  }
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace cassie

@@ -125,6 +125,21 @@ int Cassie2dBatchEnvReset(CassieBatch* h, int task, int flags, void* obs_dev, vo
  * used by state(t) (:16-19). */
 int Cassie2dBatchSetTrajectory(CassieBatch* h, const double* qpos_rows_host, int n_rows, double t_max);
 
+/* Rollout collection (BASELINE configs[4]): what rllab's sampler does around the reference env
+ * (rllab/envs/trpo_cassie.py:13-55: GaussianMLPPolicy(hidden_sizes=(32,32)).get_action ->
+ * normalize(env).step -> Cassie2dEnv.step(a, n=10)), n_policy_steps per launch for every env.
+ *   params_dev  real [n_params]: W1(obs x 32) b1 W2(32 x 32) b2 W3(32 x adim) b3 log_std(adim), the order of
+ *               rllab's get_param_values(); tanh hidden layers, linear mean, a = mean + exp(log_std) eps,
+ *               eps from Philox4x32-10 keyed by (seed, first_global_env + env, policy step of the env)
+ *   normalize   != 0: NormalizedEnv affine map [-1,1] -> [lb,ub] + clip (trpo_cassie.py:13), else clip only
+ *   outputs     obs [T][n][odim], action [T][n][adim] (raw policy output, as rllab stores it),
+ *               mean [T][n][adim], reward [T][n], done uint8 [T][n] (1 = env terminated, 2 = max_path_length);
+ *               an env whose path ended is reset to the standing pose and keeps stepping. */
+int Cassie2dBatchRollout(CassieBatch* h, int task, int mode, const void* params_dev, int n_params, int n_policy_steps,
+                         int n_substeps, int max_path_length, int flags, int normalize, unsigned long long seed,
+                         unsigned int first_global_env, void* obs_dev, void* action_dev, void* mean_dev, void* reward_dev,
+                         uint8_t* done_dev, void* stream);
+
 /* The squatting.py loop (squatting.py:8-16) on device: n_steps iterations of
  * standing_controller_jacobian (mode JACOBIAN, cassie2d.py:297-331) or
  * standing_controller_osc (mode OSC, cassie2d.py:263-295) with height target

@@ -1,0 +1,106 @@
+"""Fused rollout kernel (policy MLP + NormalizedEnv + env step, BASELINE configs[4]) on the GPU:
+the MLP against a plain PyTorch fp32 reference (tolerance 1e-5), the action noise against a numpy
+Philox4x32-10 + Box-Muller, the env transition against Cassie2dBatchEnv.step replaying the recorded
+actions, and rllab path bookkeeping (done / max_path_length)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def philox4x32_10(c, k0, k1):
+    c = [np.uint64(x) for x in c]; k0 = np.uint64(k0); k1 = np.uint64(k1); M = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c[0]; p1 = np.uint64(0xCD9E8D57) * c[2]
+        c = [((p1 >> np.uint64(32)) ^ c[1] ^ k0) & M, p1 & M, ((p0 >> np.uint64(32)) ^ c[3] ^ k1) & M, p0 & M]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & M; k1 = (k1 + np.uint64(0xBB67AE85)) & M
+    return [int(x) for x in c]
+
+
+def normal8(seed, env, step):
+    out = []
+    for b in range(2):
+        c = philox4x32_10([env, step, b, 0], seed & 0xFFFFFFFF, seed >> 32)
+        for p in range(2):
+            u1 = (np.float32(c[2 * p] >> 8) + np.float32(1)) * np.float32(1 / 16777216.0)
+            u2 = np.float32(c[2 * p + 1] >> 8) * np.float32(1 / 16777216.0)
+            rad = np.sqrt(np.float32(-2) * np.log(u1))
+            out += [rad * np.cos(np.float32(2 * np.pi) * u2), rad * np.sin(np.float32(2 * np.pi) * u2)]
+    return np.array(out, np.float64)
+
+
+@pytest.fixture(scope="module")
+def R():
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+    from cassierl_b200 import rollout
+    return rollout
+
+
+@pytest.mark.parametrize("mode,task", [("OSC", "stand"), ("PD", "stand"), ("PD", "imitate")])
+def test_policy_forward_noise_and_action_map(R, mode, task):
+    n, T = 96, 6
+    col = R.RolloutCollector(n, task=task, control_mode=mode, precision=32, seed=12345, first_global_env=1000)
+    pol = R.GaussianMLPPolicy(col.obs_dim, col.act_dim, seed=3)
+    out = col.collect(pol, T)
+    obs, act, mean = out["observations"], out["actions"], out["means"]
+    assert torch.isfinite(obs).all() and torch.isfinite(act).all()
+    ref = pol.mean(obs.reshape(-1, col.obs_dim)).reshape(T, n, col.act_dim)
+    assert float((mean - ref).abs().max() / ref.abs().max().clamp(min=1)) < 1e-5
+    eps = ((act - mean) / pol.log_std.exp()).cpu().numpy().astype(np.float64)
+    for (k, e) in ((0, 0), (0, 17), (3, 95), (5, 40)):
+        want = normal8(12345, 1000 + e, k)[:col.act_dim]
+        assert np.allclose(eps[k, e], want, atol=2e-5 * max(1.0, np.abs(want).max())), (k, e)
+    # N(0,1) sanity over all draws
+    assert abs(eps.mean()) < 0.1 and abs(eps.std() - 1.0) < 0.1
+    # sharding invariance: a sub-batch with the matching global offset reproduces its slice
+    col2 = R.RolloutCollector(32, task=task, control_mode=mode, precision=32, seed=12345, first_global_env=1000 + 64)
+    out2 = col2.collect(pol, T)
+    assert torch.equal(out2["actions"], act[:, 64:96]) and torch.equal(out2["rewards"], out["rewards"][:, 64:96])
+    col.close(); col2.close()
+
+
+def test_rollout_transitions_match_env_step(R):
+    """Replaying the recorded (normalised, clipped) actions through Cassie2dBatchEnv.step reproduces
+    the rollout's observations, rewards and dones (fp64 build, 1e-9)."""
+    from cassierl_b200 import envs
+    n, T = 16, 5
+    col = R.RolloutCollector(n, task="stand", control_mode="OSC", precision=64, seed=7)
+    pol = R.GaussianMLPPolicy(col.obs_dim, col.act_dim, seed=5, dtype=torch.float64)
+    out = col.collect(pol, T)
+    env = envs.Cassie2dBatchEnv(n, task="stand", control_mode="OSC", precision=64, auto_reset=True)
+    o = env.reset()
+    lo, hi = (torch.tensor(x, dtype=torch.float64, device=o.device) for x in env.action_space)
+    for k in range(T):
+        assert float((out["observations"][k] - o).abs().max()) < 1e-9, k
+        a = (lo + (out["actions"][k] + 1.0) * 0.5 * (hi - lo)).clamp(lo, hi)
+        o, r, d = env.step(a, n=10)
+        assert float((out["rewards"][k] - r).abs().max()) < 1e-9, k
+        assert torch.equal((out["dones"][k] == 1), d.bool()), k
+    col.close(); env.terminate()
+
+
+def test_paths_bookkeeping(R):
+    n, T = 8, 10
+    col = R.RolloutCollector(n, task="stand", control_mode="Torque", precision=32, max_path_length=4, seed=1)
+    pol = R.GaussianMLPPolicy(col.obs_dim, col.act_dim, seed=2)
+    out = col.collect(pol, T)
+    d = out["dones"].cpu().numpy()
+    paths = col.paths(pol)
+    assert sum(len(p["rewards"]) for p in paths) == n * T
+    for p in paths:
+        assert len(p["rewards"]) <= 4
+        assert p["observations"].shape == (len(p["rewards"]), 17) and p["actions"].shape == (len(p["rewards"]), 6)
+        assert p["agent_infos"]["mean"].shape == p["actions"].shape and p["agent_infos"]["log_std"].shape == p["actions"].shape
+    # with no early termination every env is cut at steps 4 and 8 by the time limit
+    for e in range(n):
+        if (d[:, e] == 1).sum() == 0:
+            assert list(np.nonzero(d[:, e])[0]) == [3, 7]
+    # the collector continues episodes across collect() calls
+    out = col.collect(pol, 2)
+    d2 = out["dones"].cpu().numpy()
+    for e in range(n):
+        if (d[:, e] == 1).sum() == 0 and (d2[:, e] == 1).sum() == 0:
+            assert list(np.nonzero(d2[:, e])[0]) == [1]
+    col.close()
