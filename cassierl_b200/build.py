@@ -10,8 +10,12 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "lib", "obj")
-LIB = os.path.join(HERE, "lib", "libcassie2d.so")
+OBJ = os.path.join(HERE, "lib", "obj" + ("_" + os.environ.get("CASSIE2D_VARIANT", "") if os.environ.get("CASSIE2D_VARIANT") else ""))
+# CASSIE2D_VARIANT=<name> + CASSIE2D_EXTRA_FLAGS="..." build an experimental copy lib/libcassie2d_<name>.so
+# (own object cache) without touching the product library; cassierl_b200.lib loads it when CASSIE2D_LIB is set.
+VARIANT = os.environ.get("CASSIE2D_VARIANT", "")
+EXTRA = os.environ.get("CASSIE2D_EXTRA_FLAGS", "").split()
+LIB = os.path.join(HERE, "lib", "libcassie2d%s.so" % ("_" + VARIANT if VARIANT else ""))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr"]
@@ -34,7 +38,10 @@ def _compile(unit, verbose):
     obj = os.path.join(OBJ, unit + ".o")
     if not _stale(obj, _deps()):
         return obj
-    cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    # fp32 kernels: approximate (2 ulp) single-precision division / sqrt -- removes the IEEE slow-path
+    # branches from the hot instruction stream (+8..30 %, profiles/r1_variants.txt); double is unaffected
+    fast = ["-prec-div=false", "-prec-sqrt=false"] if unit.endswith("_f32.cu") else []
+    cmd = [NVCC] + NVCC_FLAGS + fast + EXTRA + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
     if unit.endswith(".cpp"):
         cmd = [NVCC, "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-x", "c++", "-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)

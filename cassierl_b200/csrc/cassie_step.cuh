@@ -18,9 +18,12 @@ CASSIE_HD constexpr int action_dim(int mode) { return mode == kModeOsc ? 7 : 6; 
 // MODE is a template parameter so that each control mode gets its own register allocation.
 // The controller model may be held in a wider type TC than the physics (T): the fp32 build runs
 // the OSC controller in double (its QP is ill-conditioned, osc_qp.cuh), everything else in T.
-// mg = the physics model in the type of the position pass (planar_engine.cuh physics_step).
+// mg / mcg = the physics / controller model in the type of the position pass (planar_engine.cuh
+// physics_step): angles -> sin/cos -> pivots always run in TG (double in the fp32 build; its sincos is
+// branch-free), the result is cast to the working type.
 template <int MODE, typename T, typename TG, typename TC>
-CASSIE_HD void controller_step(const PlanarModel<T>& mp, const PlanarModel<TG>& mg, const PlanarModel<TC>& mc, T q[kNV], T qd[kNV],
+CASSIE_HD void controller_step(const PlanarModel<T>& mp, const PlanarModel<TG>& mg, const PlanarModel<TC>& mc,
+                               const PlanarModel<TG>& mcg, T q[kNV], T qd[kNV],
                                T warm[kNV], const T* act, Rows<T>& rows, T u[kNU], OpState<T>* op,
                                StepStats* st, OscStats* qst = nullptr, unsigned* qp_set = nullptr) {
   if (MODE == kModeTorque) {
@@ -41,7 +44,15 @@ CASSIE_HD void controller_step(const PlanarModel<T>& mp, const PlanarModel<TG>& 
     CASSIE_UNROLL
     for (int i = 0; i < kNV; i++) { qc[i] = (TC)q[i]; qdc[i] = (TC)qd[i]; }
     Kin<TC> kc;
-    forward_kinematics(mc, qc, qdc, kc);
+    {
+      TG qg[kNV];
+      CASSIE_UNROLL
+      for (int i = 0; i < kNV; i++) qg[i] = (TG)q[i];
+      Kin<TG> kg;
+      fk_positions(mcg, qg, kg);
+      cast_kin_positions(kg, kc);
+    }
+    fk_velocities(mc, qdc, kc);
     if (op) {
       OpState<TC> oc;
       op_state_from_kin(mc, kc, qc, oc);
@@ -61,13 +72,14 @@ CASSIE_HD void controller_step(const PlanarModel<T>& mp, const PlanarModel<TG>& 
   physics_step(mp, mg, q, qd, warm, u, rows, st);
 }
 template <typename T, typename TG, typename TC>
-CASSIE_HD void controller_step_dyn(const PlanarModel<T>& mp, const PlanarModel<TG>& mg, const PlanarModel<TC>& mc, int mode, T q[kNV], T qd[kNV],
+CASSIE_HD void controller_step_dyn(const PlanarModel<T>& mp, const PlanarModel<TG>& mg, const PlanarModel<TC>& mc,
+                                   const PlanarModel<TG>& mcg, int mode, T q[kNV], T qd[kNV],
                                    T warm[kNV], const T* act, Rows<T>& rows, T u[kNU], OpState<T>* op,
                                    StepStats* st, OscStats* qst = nullptr, unsigned* qp_set = nullptr) {
-  if (mode == kModeTorque) controller_step<kModeTorque>(mp, mg, mc, q, qd, warm, act, rows, u, op, st, qst, qp_set);
-  else if (mode == kModePd) controller_step<kModePd>(mp, mg, mc, q, qd, warm, act, rows, u, op, st, qst, qp_set);
-  else if (mode == kModeJacobian) controller_step<kModeJacobian>(mp, mg, mc, q, qd, warm, act, rows, u, op, st, qst, qp_set);
-  else controller_step<kModeOsc>(mp, mg, mc, q, qd, warm, act, rows, u, op, st, qst, qp_set);
+  if (mode == kModeTorque) controller_step<kModeTorque>(mp, mg, mc, mcg, q, qd, warm, act, rows, u, op, st, qst, qp_set);
+  else if (mode == kModePd) controller_step<kModePd>(mp, mg, mc, mcg, q, qd, warm, act, rows, u, op, st, qst, qp_set);
+  else if (mode == kModeJacobian) controller_step<kModeJacobian>(mp, mg, mc, mcg, q, qd, warm, act, rows, u, op, st, qst, qp_set);
+  else controller_step<kModeOsc>(mp, mg, mc, mcg, q, qd, warm, act, rows, u, op, st, qst, qp_set);
 }
 
 // standing_controller_jacobian (cassie2d.py:297-331): s = GetOperationalSpaceState array

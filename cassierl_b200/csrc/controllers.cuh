@@ -108,7 +108,7 @@ CASSIE_HD void pivot_accelerations(const Kin<T>& k, PivotAcc<T>& pa) {
 // symmetric 4x4 pseudo-inverse with singular-value cut-off (HelperFunctions.h:8-29 applied to
 // Jeq M^-1 Jeq^T, which is symmetric PSD: singular values = eigenvalues).  Cyclic Jacobi.
 template <typename T>
-CASSIE_HD void sym4_pinv(T A[4][4], T tol, T P[4][4]) {
+CASSIE_COLD void sym4_pinv_jacobi(T A[4][4], T tol, T P[4][4]) {
   T V[4][4];
   CASSIE_UNROLL
   for (int i = 0; i < 4; i++) {
@@ -181,7 +181,7 @@ CASSIE_HD void sym4_pinv(T A[4][4], T tol, T P[4][4]) {
 // u = pinv(B, tol) * rhs for a 13x6 matrix B (Cassie2d.cpp:165, default tolerance 1e-4):
 // one-sided Jacobi, B V = U S ;  u = sum_j v_j (b_j . rhs) / s_j^2 over s_j > tol.
 template <typename T>
-CASSIE_HD void pinv13x6_apply(T B[kNV][kNU], T tol, const T rhs[kNV], T u[kNU]) {
+CASSIE_COLD void pinv13x6_apply_jacobi(T B[kNV][kNU], T tol, const T rhs[kNV], T u[kNU]) {
   T V[kNU][kNU];
   CASSIE_UNROLL
   for (int i = 0; i < kNU; i++) {
@@ -236,6 +236,128 @@ CASSIE_HD void pinv13x6_apply(T B[kNV][kNU], T tol, const T rhs[kNV], T u[kNU]) 
       CASSIE_UNROLL
       for (int i = 0; i < kNU; i++) u[i] += V[i][j] * w;
     }
+  }
+}
+
+// Fast paths of the two pseudo-inverses.  pseudoinverse(A, tol) zeroes singular values <= tol
+// (HelperFunctions.h:8-29); when ALL singular values exceed tol it is the plain inverse / least-squares
+// solution.  Both routines certify that case with the bound  sigma_min >= 1 / ||A^-1||_F  and otherwise
+// fall back to the (out-of-line) Jacobi SVD, so the result is the reference's in every case while the
+// hot instruction stream carries a Cholesky / QR instead of ~60 Jacobi rotations.
+template <typename T>
+CASSIE_HD void sym4_pinv(T A[4][4], T tol, T P[4][4]) {
+  // Cholesky A = L L^T, P = L^-T L^-1
+  T L[4][4], Li[4][4];
+  bool ok = true;
+  CASSIE_UNROLL
+  for (int i = 0; i < 4; i++) {
+    CASSIE_UNROLL
+    for (int j = 0; j < 4; j++) {
+      if (j <= i) {
+        T sacc = A[i][j];
+        CASSIE_UNROLL
+        for (int k = 0; k < 4; k++)
+          if (k < j) sacc -= L[i][k] * L[j][k];
+        if (i == j) {
+          ok = ok && (sacc > T(0));
+          L[i][i] = Num<T>::sqrt_(sacc > T(0) ? sacc : T(1));
+        } else {
+          L[i][j] = sacc / L[j][j];
+        }
+      }
+    }
+  }
+  T fro = T(0);
+  CASSIE_UNROLL
+  for (int j = 0; j < 4; j++) {  // column j of L^-1
+    CASSIE_UNROLL
+    for (int i = 0; i < 4; i++) {
+      if (i < j) Li[i][j] = T(0);
+      else {
+        T sacc = i == j ? T(1) : T(0);
+        CASSIE_UNROLL
+        for (int k = 0; k < 4; k++)
+          if (k >= j && k < i) sacc -= L[i][k] * Li[k][j];
+        Li[i][j] = sacc / L[i][i];
+      }
+    }
+  }
+  CASSIE_UNROLL
+  for (int i = 0; i < 4; i++) {
+    CASSIE_UNROLL
+    for (int j = 0; j < 4; j++) {
+      T sacc = T(0);
+      CASSIE_UNROLL
+      for (int k = 0; k < 4; k++)
+        if (k >= i && k >= j) sacc += Li[k][i] * Li[k][j];
+      P[i][j] = sacc;
+      fro += sacc * sacc;
+    }
+  }
+  // all eigenvalues > tol  <=>  certified by  1/||A^-1||_F > tol  (margin 2x for rounding)
+  if (!ok || !(fro * (T(2) * tol) * (T(2) * tol) < T(1))) sym4_pinv_jacobi(A, tol, P);
+}
+
+template <typename T>
+CASSIE_HD void pinv13x6_apply(T B[kNV][kNU], T tol, const T rhs[kNV], T u[kNU]) {
+  // modified Gram-Schmidt QR, B = Q R (Q overwrites a copy of B)
+  T Q[kNV][kNU], R[kNU][kNU], y[kNU];
+  CASSIE_UNROLL
+  for (int i = 0; i < kNV; i++) {
+    CASSIE_UNROLL
+    for (int j = 0; j < kNU; j++) Q[i][j] = B[i][j];
+  }
+  bool ok = true;
+  CASSIE_UNROLL
+  for (int j = 0; j < kNU; j++) {
+    T nn = T(0);
+    CASSIE_UNROLL
+    for (int i = 0; i < kNV; i++) nn += Q[i][j] * Q[i][j];
+    ok = ok && (nn > T(1e-30));
+    const T rjj = Num<T>::sqrt_(nn > T(1e-30) ? nn : T(1));
+    const T inv = T(1) / rjj;
+    R[j][j] = rjj;
+    T d = T(0);
+    CASSIE_UNROLL
+    for (int i = 0; i < kNV; i++) { Q[i][j] *= inv; d += Q[i][j] * rhs[i]; }
+    y[j] = d;
+    CASSIE_UNROLL
+    for (int k = 0; k < kNU; k++) {
+      if (k > j) {
+        T rjk = T(0);
+        CASSIE_UNROLL
+        for (int i = 0; i < kNV; i++) rjk += Q[i][j] * Q[i][k];
+        R[j][k] = rjk;
+        CASSIE_UNROLL
+        for (int i = 0; i < kNV; i++) Q[i][k] -= rjk * Q[i][j];
+      }
+    }
+  }
+  // R^-1 (upper triangular) for the certificate and the solve
+  T Ri[kNU][kNU], fro = T(0);
+  CASSIE_UNROLL
+  for (int j = kNU - 1; j >= 0; j--) {
+    CASSIE_UNROLL
+    for (int i = kNU - 1; i >= 0; i--) {
+      if (i > j) Ri[i][j] = T(0);
+      else {
+        T sacc = i == j ? T(1) : T(0);
+        CASSIE_UNROLL
+        for (int k = 0; k < kNU; k++)
+          if (k > i && k <= j) sacc -= R[i][k] * Ri[k][j];
+        Ri[i][j] = sacc / R[i][i];
+      }
+      fro += Ri[i][j] * Ri[i][j];
+    }
+  }
+  if (!ok || !(fro * (T(2) * tol) * (T(2) * tol) < T(1))) { pinv13x6_apply_jacobi(B, tol, rhs, u); return; }
+  CASSIE_UNROLL
+  for (int i = 0; i < kNU; i++) {
+    T sacc = T(0);
+    CASSIE_UNROLL
+    for (int k = 0; k < kNU; k++)
+      if (k >= i) sacc += Ri[i][k] * y[k];
+    u[i] = sacc;
   }
 }
 

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ ModelPa
   OscStats qs = {0, 0};
   unsigned qps = v.qp_set[e];
   for (int s = 0; s < n_sub; s++)
-    controller_step<MODE>(mp.phys, mp.phys_d, ctrl_model<MODE>(mp), q, qd, w, act, rows, u, s == n_sub - 1 ? &op : nullptr, &st, &qs, &qps);
+    controller_step<MODE>(mp.phys, mp.phys_d, ctrl_model<MODE>(mp), mp.ctrl_d, q, qd, w, act, rows, u, s == n_sub - 1 ? &op : nullptr, &st, &qs, &qps);
   v.qp_set[e] = qps;
   store_env(v, e, q, qd, w);
   if (n_sub > 0) {
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kBlock) k_env_step(const __grid_constant__ Mod
   double t = v.clock[e];
   unsigned qps = v.qp_set[e];
   for (int s = 0; s < a.n_sub; s++) {
-    controller_step<MODE>(mp.phys, mp.phys_d, ctrl_model<MODE>(mp), q, qd, w, act, rows, u, s == a.n_sub - 1 ? &op : nullptr, &st, &qs, &qps);
+    controller_step<MODE>(mp.phys, mp.phys_d, ctrl_model<MODE>(mp), mp.ctrl_d, q, qd, w, act, rows, u, s == a.n_sub - 1 ? &op : nullptr, &st, &qs, &qps);
     t += 0.0005;  // cassie2d.py:122
   }
   T o18[18], ref9[9], r;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kBlock) k_squat(const __grid_constant__ ModelP
     const T zt = (T)(0.7 + 0.25 * sn), zdt = (T)(0.25 * cs);
     if (MODE == kModeJacobian) squat_jacobian_action(o18, zt, zdt, act);
     else squat_osc_action(o18, zt, zdt, act);
-    controller_step<MODE>(mp.phys, mp.phys_d, ctrl_model<MODE>(mp), q, qd, w, act, rows, u, &op, &st, &qs, &qps);
+    controller_step<MODE>(mp.phys, mp.phys_d, ctrl_model<MODE>(mp), mp.ctrl_d, q, qd, w, act, rows, u, &op, &st, &qs, &qps);
     t = t + 0.0005;  // squatting.py:15
   }
   v.clock[e] = t;

@@ -17,9 +17,11 @@
 
 #if defined(__CUDACC__)
 #define CASSIE_HD __host__ __device__ __forceinline__
+#define CASSIE_COLD __host__ __device__ __noinline__
 #define CASSIE_UNROLL _Pragma("unroll")
 #else
 #define CASSIE_HD inline
+#define CASSIE_COLD inline
 #define CASSIE_UNROLL
 #endif
 
@@ -474,7 +476,10 @@ CASSIE_HD void constraint_positions(const PlanarModel<TG>& m, const Kin<TG>& k, 
 // mj_collision + mj_makeConstraint + mj_makeImpedance [EXT], canonical row order:
 // connects (L, R), joint limits (dof order), contacts (pelvis sphere, then per capsule the 'to'
 // end before the 'from' end).  Returns the public contact bit mask.
-template <typename T>
+// ALL = false builds only the rows of the common regime (connects + the four toe-capsule end spheres);
+// the caller guarantees that nothing else is active (rare_rows_active), so both variants emit the
+// same rows in the same order there.
+template <bool ALL, typename T>
 CASSIE_HD unsigned int make_rows(const PlanarModel<T>& m, const Kin<T>& k, const ConPos<T>& cp, const T* q, const T* qd,
                                   Rows<T>& r, int* nlimit) {
   r.n = 0;
@@ -501,7 +506,7 @@ CASSIE_HD unsigned int make_rows(const PlanarModel<T>& m, const Kin<T>& k, const
   kb_from_solref(m, m.lim_solref, m.lim_solimp, K, Bd);
   CASSIE_UNROLL
   for (int j = 3; j < kNV; j++) {
-    if (m.has_limit[j]) {
+    if (ALL && m.has_limit[j]) {
       const T dlo = q[j] - m.lim_lo[j], dhi = m.lim_hi[j] - q[j];
       CASSIE_UNROLL
       for (int side = 0; side < 2; side++) {
@@ -524,7 +529,7 @@ CASSIE_HD unsigned int make_rows(const PlanarModel<T>& m, const Kin<T>& k, const
     T cx, cz;
     rot(k.c0, k.s0, m.sph_c[0], m.sph_c[1], cx, cz);
     const T dist = cp.sph_dist;
-    if (!(dist > T(0))) {
+    if (ALL && !(dist > T(0))) {
       T Jx[8], Jz[8];
       point_jac(m, k, 0, -1, cx, cz - m.sph_r - T(0.5) * dist, Jx, Jz);
       const T imp = impedance(m.con_solimp, dist);
@@ -544,7 +549,7 @@ CASSIE_HD unsigned int make_rows(const PlanarModel<T>& m, const Kin<T>& k, const
         const T* ep = e ? m.cap_from[cap] : m.cap_to[cap];
         rot(k.c[L][g], k.s[L][g], ep[0], ep[1], ex, ez);
         const T dist = cp.cap_dist[cap][e];
-        if (!(dist > T(0))) {
+        if ((ALL || g == kToe) && !(dist > T(0))) {
           T Jx[8], Jz[8];
           point_jac(m, k, L, g, ex, ez - m.cap_r[cap] - T(0.5) * dist, Jx, Jz);
           const T imp = impedance(m.con_solimp, dist);
@@ -875,6 +880,34 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
   return iter;
 }
 
+// Anything outside the common regime active?  (a violated joint limit, or a floor contact of the
+// pelvis sphere / thigh / shin / tarsus capsules)
+template <typename T>
+CASSIE_HD bool rare_rows_active(const PlanarModel<T>& m, const ConPos<T>& cp, const T* q) {
+  bool rare = !(cp.sph_dist > T(0));
+  CASSIE_UNROLL
+  for (int L = 0; L < 2; L++) {
+    CASSIE_UNROLL
+    for (int g = 0; g < 3; g++) rare = rare || !(cp.cap_dist[4 * L + g][0] > T(0)) || !(cp.cap_dist[4 * L + g][1] > T(0));
+  }
+  CASSIE_UNROLL
+  for (int j = 3; j < kNV; j++)
+    if (m.has_limit[j]) rare = rare || (q[j] - m.lim_lo[j] < T(0)) || (m.lim_hi[j] - q[j] < T(0));
+  return rare;
+}
+
+// Out-of-line slow path: all row kinds, any row count, thread-local memory.  Kept out of the hot
+// instruction stream on purpose: inlined, its mere presence cost the Jacobian-mode kernel 30 % (register
+// allocation + instruction fetch; profiles/r1_variants.txt).
+template <typename T>
+CASSIE_COLD void constraints_cold(const PlanarModel<T>& m, const Kin<T>& k, const ConPos<T>& cp, const T* q, const T* qd,
+                                  Rows<T>& r, const T (&LD)[kNV][kNV], const T* Dinv, const T* qs, const T* warm, T* fc,
+                                  int* sweeps, unsigned int* mask) {
+  int nlimit = 0;
+  *mask = make_rows<true>(m, k, cp, q, qd, r, &nlimit);
+  *sweeps = constraint_solve_general(m, r, LD, Dinv, qs, warm, fc);
+}
+
 // One mj_step [EXT] (Cassie2d.cpp:92): forward dynamics, constraint solve, semi-implicit Euler
 // with implicit joint damping.  q, qd, warm are updated in place; u is in ctrl units.
 // TG = type of the position pass (angles -> sin/cos -> pivots -> constraint violations): double in
@@ -920,27 +953,29 @@ CASSIE_HD void physics_step(const PlanarModel<T>& m, const PlanarModel<TG>& mg, 
   for (int i = 0; i < kNV; i++) qs[i] = fs[i];
   solve(LD, Dinv, qs);
 
-  int nlimit = 0;
-  const unsigned int mask = make_rows(m, k, cp, q, qd, r, &nlimit);
-  const int n = r.n;
   T fc[kNV];  // qfrc_constraint = J^T f
   int sweeps;
+  unsigned int mask;
 #ifdef CASSIE_HOST_HARNESS  // test hook: lets the harness exercise / count the general path on small row counts
   const bool fast_ok = !cassie_force_general_path;
 #else
   const bool fast_ok = true;
 #endif
-  if (fast_ok && nlimit == 0 && n <= kFastRows) {
+  if (fast_ok && !rare_rows_active(m, cp, q)) {
+    // common regime: 4 connect rows + <= 4 toe contacts, everything in registers
+    mask = make_rows<false>(m, k, cp, q, qd, r, (int*)nullptr);
     // 8-row (two contacts) or 12-row variant, chosen per WARP so that lanes never run both
 #ifdef __CUDA_ARCH__
-    const bool wide = __any_sync(__activemask(), n > 8);
+    const bool wide = __any_sync(__activemask(), r.n > 8);
 #else
-    const bool wide = n > 8;
+    const bool wide = r.n > 8;
 #endif
     if (wide) sweeps = constraint_solve_fast<4>(m, r, LD, Dinv, qs, warm, fc);
     else sweeps = constraint_solve_fast<2>(m, r, LD, Dinv, qs, warm, fc);
+  } else {
+    constraints_cold(m, k, cp, q, qd, r, LD, Dinv, qs, warm, fc, &sweeps, &mask);
   }
-  else sweeps = constraint_solve_general(m, r, LD, Dinv, qs, warm, fc);
+  const int n = r.n;
   // qacc = qacc_smooth + M^-1 qfrc_constraint
   T dq[kNV];
   CASSIE_UNROLL

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kBlock) k_rollout(const __grid_constant__ Mode
     }
     // ---- Cassie2dEnv.step(action, n)
     for (int s = 0; s < a.n_sub; s++) {
-      controller_step<MODE>(mp.phys, mp.phys_d, ctrl_model<MODE>(mp), q, qd, w, act, rows, u, s == a.n_sub - 1 ? &op : nullptr, &st, &qs, &qps);
+      controller_step<MODE>(mp.phys, mp.phys_d, ctrl_model<MODE>(mp), mp.ctrl_d, q, qd, w, act, rows, u, s == a.n_sub - 1 ? &op : nullptr, &st, &qs, &qps);
       t += 0.0005;
     }
     T r;

@@ -7,7 +7,7 @@ from .structs import (ControllerForce, ControllerOsc, ControllerPd, ControllerTo
                       StateOperationalSpace)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcassie2d.so")
+LIB_PATH = os.environ.get("CASSIE2D_LIB") or os.path.join(_HERE, "lib", "libcassie2d.so")
 
 MODE_TORQUE, MODE_PD, MODE_JACOBIAN, MODE_OSC = 0, 1, 2, 3
 TASK_STAND, TASK_IMITATE = 0, 1

@@ -96,8 +96,18 @@ static int gauss_solve(int n, double* A, double* b) {
  * Stands in for qpOASES::SQProblem::init/hotstart (OSC_RBDL.cpp:275-278): returns the exact
  * optimum (the reference's wall-clock cut-off of the hot start is not reproducible).
  * Constraints are normalised to  a_k' x <= b_k.  Needs a feasible start in x. */
+static int qp_solve_ws(int n, int mc, const double* G, const double* g, const double* A,
+                       const double* lbA, const double* ubA, const double* lb, const double* ub, double* x,
+                       int* ws, int* nws);
 int orc_qp_solve(int n, int mc, const double* G, const double* g, const double* A,
                  const double* lbA, const double* ubA, const double* lb, const double* ub, double* x) {
+  return qp_solve_ws(n, mc, G, g, A, lbA, ubA, lb, ub, x, NULL, NULL);
+}
+/* ws/nws (optional): working set carried from the previous solve of a QP with the same constraints --
+ * the qpOASES hot start of the reference (OSC_RBDL.cpp:278); x must then be the previous solution. */
+static int qp_solve_ws(int n, int mc, const double* G, const double* g, const double* A,
+                       const double* lbA, const double* ubA, const double* lb, const double* ub, double* x,
+                       int* ws, int* nws) {
   const double INF = 1e30;
   int maxk = 2 * n + 2 * mc;
   double* ca = (double*)calloc((size_t)maxk * n, sizeof(double));
@@ -111,8 +121,20 @@ int orc_qp_solve(int n, int mc, const double* G, const double* g, const double* 
     if (ubA && ubA[r] < INF) { for (int i = 0; i < n; i++) ca[nk * n + i] = A[r * n + i]; cb[nk++] = ubA[r]; }
     if (lbA && lbA[r] > -INF) { for (int i = 0; i < n; i++) ca[nk * n + i] = -A[r * n + i]; cb[nk++] = -lbA[r]; }
   }
+  /* anti-stalling: the friction pyramids have degenerate vertices (at the apex beta_z = 0 nine
+   * constraints meet in five dimensions) where a textbook active-set method stalls for hundreds of
+   * zero-length steps; relaxing each right-hand side by a distinct amount of order 1e-11 splits them */
+  for (int k2 = 0; k2 < nk; k2++) cb[k2] += 1e-11 * (1.0 + fmod(0.6180339887 * (k2 + 1), 1.0));
   int* W = (int*)calloc(nk + 1, sizeof(int));
   int nw = 0, iter, rc = -1;
+  if (ws && nws) { /* keep only constraints that are still active at x */
+    for (int w = 0; w < *nws && w < nk; w++) {
+      int k2 = ws[w];
+      double ax = 0;
+      for (int j = 0; j < n; j++) ax += ca[k2 * n + j] * x[j];
+      if (fabs(ax - cb[k2]) <= 1e-9 * (1.0 + fabs(cb[k2]))) W[nw++] = k2;
+    }
+  }
   int dim = n + nk;
   double* K = (double*)malloc(sizeof(double) * dim * dim);
   double* rhs = (double*)malloc(sizeof(double) * dim);
@@ -150,7 +172,7 @@ int orc_qp_solve(int n, int mc, const double* G, const double* g, const double* 
     if (singular) { rc = -2; break; }
     double pn = 0, xn = 1;
     for (int i = 0; i < n; i++) { pn = fmax(pn, fabs(rhs[i])); xn = fmax(xn, fabs(x[i])); }
-    if (pn <= 1e-12 * xn) {
+    if (pn <= 1e-9 * xn) { /* cond(G) ~ 1e10: the Newton step of the working set carries ~1e-6 relative noise */
       /* stationary on the working set: check multipliers (lambda >= 0 for a'x <= b) */
       int worst = -1; double wv = -1e-10;
       for (int w = 0; w < nw; w++) if (rhs[n + w] < wv) { wv = rhs[n + w]; worst = w; }
@@ -175,6 +197,7 @@ int orc_qp_solve(int n, int mc, const double* G, const double* g, const double* 
     for (int i = 0; i < n; i++) x[i] += alpha * rhs[i];
     if (block >= 0) W[nw++] = block;
   }
+  if (ws && nws) { *nws = nw; for (int w = 0; w < nw; w++) ws[w] = W[w]; }
   free(ca); free(cb); free(W); free(K); free(rhs);
   return rc;
 }
@@ -188,6 +211,7 @@ struct orc_cassie {
   double last_u[NUU];
   double osc_x[NX], osc_obj;
   int osc_iters;
+  double qp_z[26]; int qp_ws[128], qp_nws, qp_started; /* QP hot-start state (survives Reset, App. D.3) */
   int contact_sites[NCON]; /* {2,3,4,5} Cassie2d.cpp:34 */
   int target_sites[5];     /* {1..5}    Cassie2d.cpp:35-36 */
 };
@@ -472,10 +496,25 @@ void orc_cassie_step_osc(orc_cassie* c, const double act[7]) {
   for (int r = 0; r < 32; r++) { ubA[r] = 0; lbA[r] = -1e300; }
   for (int a = 0; a < NUU; a++) { lb[a] = m->act_range[a][0]; ub[a] = m->act_range[a][1]; }
   for (int i = NUU; i < NZ; i++) { lb[i] = 0; ub[i] = 1e300; }
-  /* strictly feasible start */
+  /* first call: strictly feasible start ("init"); afterwards hot start from the previous solution and
+   * working set (OSC_RBDL.cpp:275-278) -- the constraints never change, so it stays feasible */
   double z[NZ] = {0};
-  for (int i = 0; i < NCON; i++) { for (int j = 0; j < 4; j++) z[NUU + i * 5 + j] = 0.1; z[NUU + i * 5 + 4] = 1.0; }
-  c->osc_iters = orc_qp_solve(NZ, 32, G, gz, C, lbA, ubA, lb, ub, z);
+  if (!c->qp_started) {
+    for (int i = 0; i < NCON; i++) { for (int j = 0; j < 4; j++) z[NUU + i * 5 + j] = 0.1; z[NUU + i * 5 + 4] = 1.0; }
+    c->qp_nws = 0;
+  } else {
+    memcpy(z, c->qp_z, sizeof(z));
+  }
+  c->osc_iters = qp_solve_ws(NZ, 32, G, gz, C, lbA, ubA, lb, ub, z, c->qp_ws, &c->qp_nws);
+  if (c->osc_iters < 0) { /* cap or failure: restart cold once */
+    memset(z, 0, sizeof(z));
+    for (int i = 0; i < NCON; i++) { for (int j = 0; j < 4; j++) z[NUU + i * 5 + j] = 0.1; z[NUU + i * 5 + 4] = 1.0; }
+    c->qp_nws = 0;
+    int it2 = qp_solve_ws(NZ, 32, G, gz, C, lbA, ubA, lb, ub, z, c->qp_ws, &c->qp_nws);
+    if (it2 >= 0) c->osc_iters = it2;
+  }
+  memcpy(c->qp_z, z, sizeof(z));
+  c->qp_started = 1;
   /* recover x = [qdd; u; beta] and the objective 1/2 x'Hx + g'x */
   double qdd[NQ];
   for (int i = 0; i < NQ; i++) { double s = p0[i]; for (int j = 0; j < NZ; j++) s += P[i * NZ + j] * z[j]; qdd[i] = s; }

@@ -81,7 +81,7 @@ static void ctrl_step(int mode, int n, double* q, double* qd, double* warm, cons
     OpState<T> op;
     StepStats st;
     OscStats qs = {0, 0};
-    controller_step_dyn(mp, g_models.phys, mc, mode, tq, tv, tw, a, rows, u, &op, &st, &qs, &qp_set);
+    controller_step_dyn(mp, g_models.phys, mc, g_models.ctrl, mode, tq, tv, tw, a, rows, u, &op, &st, &qs, &qp_set);
     if (u_out) for (int i = 0; i < kNU; i++) u_out[s * kNU + i] = u[i];
     if (op_out) {
       T o[18];
@@ -120,7 +120,7 @@ static void squat(int mode, int n, double phase, double* q, double* qd, double* 
     if (mode == kModeJacobian) squat_jacobian_action(o, zt, zdt, a);
     else squat_osc_action(o, zt, zdt, a);
     OscStats qs = {0, 0};
-    controller_step_dyn(mp, g_models.phys, mc, mode, tq, tv, tw, a, rows, u, &op, (StepStats*)nullptr, &qs, &qp_set);
+    controller_step_dyn(mp, g_models.phys, mc, g_models.ctrl, mode, tq, tv, tw, a, rows, u, &op, (StepStats*)nullptr, &qs, &qp_set);
     if (qp_out) { qp_out[2 * s] = qs.iters; qp_out[2 * s + 1] = qs.status; }
     t = t + 0.0005;
     if (traj_out) for (int i = 0; i < kNV; i++) { traj_out[s * 26 + i] = tq[i]; traj_out[s * 26 + 13 + i] = tv[i]; }
@@ -150,13 +150,24 @@ void hh_count_ops(int mode, const double* q, const double* qd, const double* war
   g_ops = OpCount();
   OscStats qs = {0, 0};
   unsigned qp_set = (unsigned)out[8];   // in: warm-start partition, out: QP iterations
-  controller_step_dyn(mp, mg, mc, mode, tq, tv, tw, a, rows, u, &op, &st, &qs, &qp_set);
+  controller_step_dyn(mp, mg, mc, mc, mode, tq, tv, tw, a, rows, u, &op, &st, &qs, &qp_set);
   out[8] = qs.iters; out[9] = qp_set;
   out[0] = g_ops.add; out[1] = g_ops.mul; out[2] = g_ops.div; out[3] = g_ops.sqrt_; out[4] = g_ops.trig; out[5] = g_ops.cmp;
   out[6] = st.nrows; out[7] = st.sweeps;
 }
 
 void hh_force_general_path(int on) { cassie_force_general_path = on != 0; }
+// the two pseudo-inverse routines of controllers.cuh (fast Cholesky / QR path + certified Jacobi fallback)
+void hh_sym4_pinv(const double* A, double tol, double* P, int f32) {
+  if (f32) { float a[4][4], p[4][4]; for (int i = 0; i < 16; i++) a[i / 4][i % 4] = (float)A[i]; sym4_pinv(a, (float)tol, p); for (int i = 0; i < 16; i++) P[i] = p[i / 4][i % 4]; }
+  else { double a[4][4], p[4][4]; for (int i = 0; i < 16; i++) a[i / 4][i % 4] = A[i]; sym4_pinv(a, tol, p); for (int i = 0; i < 16; i++) P[i] = p[i / 4][i % 4]; }
+}
+void hh_pinv13x6_apply(const double* B, double tol, const double* rhs, double* u) {
+  double b[kNV][kNU], r[kNV], uu[kNU];
+  for (int i = 0; i < kNV; i++) { r[i] = rhs[i]; for (int j = 0; j < kNU; j++) b[i][j] = B[i * kNU + j]; }
+  pinv13x6_apply(b, tol, r, uu);
+  for (int j = 0; j < kNU; j++) u[j] = uu[j];
+}
 int hh_load(const char* path) { return flatten_mjcf_file(path, &g_models, &g_err) ? 0 : -1; }
 const char* hh_error() { return g_err.c_str(); }
 const void* hh_model(int ctrl) { return ctrl ? &g_models.ctrl : &g_models.phys; }

@@ -218,3 +218,28 @@ def test_osc_phases_match_oracle_rollout(harness, oracle, omodel):
         harness.squat(3, steps, phase[e], q, qd, w)
         assert rel_err(oracle.state26_from_qpos_qvel(q, qd), ref[e]) < 1e-4, e
         assert harness.last_qp[:, 1].max() == 0
+
+
+def test_pseudo_inverse_fast_paths_and_fallbacks(harness):
+    """controllers.cuh: Cholesky / QR fast paths give pinv when every singular value exceeds the
+    reference's cut-off (HelperFunctions.h:8-29) and hand over to the Jacobi SVD otherwise."""
+    import ctypes as ct
+    rng = np.random.default_rng(4)
+    P = np.zeros((4, 4))
+    for case in range(6):
+        X = rng.standard_normal((4, 4))
+        S = X @ X.T + 0.3 * np.eye(4)
+        if case >= 3:   # one eigenvalue below the 1e-3 cut-off -> must be zeroed, not inverted
+            w, V = np.linalg.eigh(S); w[0] = 2e-4 * (case - 2); S = (V * w) @ V.T
+        harness.L.hh_sym4_pinv(harness.p(np.ascontiguousarray(S)), ct.c_double(1e-3), harness.p(P), 0)
+        w, V = np.linalg.eigh(S)
+        ref = (V[:, w > 1e-3] / w[w > 1e-3]) @ V[:, w > 1e-3].T
+        np.testing.assert_allclose(P, ref, atol=1e-9 * np.abs(ref).max())
+    u = np.zeros(6)
+    for case in range(4):
+        B = rng.standard_normal((13, 6)) * np.array([16, 16, 100, 16, 16, 100.0])
+        if case >= 2:   # rank deficient: two identical columns
+            B[:, 3] = B[:, 0]
+        rhs = rng.standard_normal(13)
+        harness.L.hh_pinv13x6_apply(harness.p(np.ascontiguousarray(B)), ct.c_double(1e-4), harness.p(rhs), harness.p(u))
+        np.testing.assert_allclose(u, np.linalg.pinv(B, rcond=1e-12) @ rhs, atol=1e-9)

@@ -289,7 +289,7 @@ def test_env_step_stand_fp64(E, LIB, oracle, omodel, mode):
         for e, c in enumerate(refs):
             qo, vo = c.data.state()
             assert rel_err(np.concatenate([q[e], v[e]]), np.concatenate([qo, vo])) < 1e-8, (k, e)
-    assert n_done > 0 or mode == 3   # random torque/PD policies fall within the horizon: auto-reset is exercised
+    assert n_done > 0 or mode != 0   # random torques make the robot fall within the horizon: auto-reset is exercised
     env.terminate()
 
 
