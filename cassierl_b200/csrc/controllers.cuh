@@ -372,6 +372,7 @@ struct CtrlDyn {
   T bias[kNV];                 // C + G + D qd   (DynamicState.cpp:49-52)
   T Jeq[4][8];                 // rows: L x, L z, R x, R z in J8 layout
   T JH[4][kNV], T1[kNV][4], gamma[kNV];
+  T sjd[4];                    // pinv(Jeq M^-1 Jeq^T) JeqdotQdot
 };
 
 template <typename T>
@@ -458,6 +459,13 @@ CASSIE_HD void ctrl_dynamics(const PlanarModel<T>& m, const Kin<T>& k, const T* 
     CASSIE_UNROLL
     for (int r = 0; r < 4; r++) s += d.T1[i][r] * jd[r];
     d.gamma[i] = s;
+  }
+  CASSIE_UNROLL
+  for (int r = 0; r < 4; r++) {
+    T s = T(0);
+    CASSIE_UNROLL
+    for (int c = 0; c < 4; c++) s += P[r][c] * jd[c];
+    d.sjd[r] = s;
   }
 }
 

@@ -42,8 +42,8 @@ CASSIE_HD void box_qp_solve(const double G[kQpN][kQpN], const double g[kQpN], co
   double L[kQpN][kQpN], grad[kQpN];
   double gscale = 1.0;
   for (int i = 0; i < kQpN; i++) gscale = fmax(gscale, fabs(g[i]));
-  const double dtol = 1e-10 * gscale;
-  int it = 0, status = 1, best = kQpN + 1, budget = 3;
+  const double dtol = 1e-12 * gscale;
+  int it = 0, status = 1, best = kQpN + 1, budget = 10;
   for (; it < max_iter; it++) {
     const unsigned fixed = at_lo | at_hi;
     for (int i = 0; i < kQpN; i++) z[i] = ((at_lo >> i) & 1u) ? lo[i] : (((at_hi >> i) & 1u) ? hi[i] : 0.0);
@@ -85,6 +85,12 @@ CASSIE_HD void box_qp_solve(const double G[kQpN][kQpN], const double g[kQpN], co
     // violations: free variables outside their bounds, pinned variables with a wrong-sign multiplier
     unsigned viol = 0u;
     int nviol = 0, last = -1;
+    // cond(G) ~ 1e10: a degenerate variable (true value 0, true multiplier 0) comes out as +-1e-6 of the
+    // solution scale, so feasibility is judged with a tolerance relative to that scale -- otherwise it
+    // flips between "free" and "pinned" forever
+    double zmax = 1.0;
+    for (int i = 0; i < kQpN; i++) zmax = fmax(zmax, fabs(z[i]));
+    const double ptol = 1e-8 * zmax;
     for (int i = 0; i < kQpN; i++) {
       bool bad;
       if ((fixed >> i) & 1u) {
@@ -92,13 +98,12 @@ CASSIE_HD void box_qp_solve(const double G[kQpN][kQpN], const double g[kQpN], co
         for (int j = 0; j < kQpN; j++) s += G[i][j] * z[j];
         bad = ((at_lo >> i) & 1u) ? (s < -dtol) : (s > dtol);
       } else {
-        const double ptol = 1e-12 * fmax(1.0, fabs(z[i]));
         bad = z[i] < lo[i] - ptol || z[i] > hi[i] + ptol;
       }
       if (bad) { viol |= 1u << i; nviol++; last = i; }
     }
     if (nviol == 0) { status = 0; it++; break; }
-    if (nviol < best) { best = nviol; budget = 3; }
+    if (nviol < best) { best = nviol; budget = 10; }
     else if (budget > 0) budget--;
     else viol = 1u << last;
     for (int i = 0; i < kQpN; i++) {
@@ -152,54 +157,63 @@ CASSIE_HD void osc_control(const PlanarModel<T>& m, const Kin<T>& k, const T* qd
   e0[10] = -act[6];
   aleg[10] = 0;
   W[10] = kOscWRest;
-  // ---- P columns: qdd = P z + p0.  Columns 0..5 u, then per contact site (fx, fz)
-  T P[kQpN + 1][kNV];
-  CASSIE_UNROLL
-  for (int a = 0; a < kNU; a++) {
-    CASSIE_UNROLL
-    for (int i = 0; i < kNV; i++) P[a][i] = m.act_dof[a] == i ? m.act_gear[a] : T(0);
-  }
-  CASSIE_UNROLL
-  for (int s = 0; s < 4; s++) {
-    expand_row(A[2 + 2 * s], s / 2, P[kNU + 2 * s]);       // Jc^T e_x of site s  (DynamicState.cpp:57-62)
-    expand_row(A[3 + 2 * s], s / 2, P[kNU + 2 * s + 1]);   // Jc^T e_z
-  }
-  CASSIE_UNROLL
-  for (int i = 0; i < kNV; i++) P[kQpN][i] = -d.bias[i];
-  for (int j = 0; j <= kQpN; j++) {
-    apply_Nc(d, P[j]);
-    if (j == kQpN) {
-      CASSIE_UNROLL
-      for (int i = 0; i < kNV; i++) P[j][i] -= d.gamma[i];
-    }
-    solve(d.LD, d.Dinv, P[j]);
-  }
-  // ---- E = A P (tasks x variables), e0 += A p0 ; then the cone generators l1, l2 per contact
-  double E[kQpTasks][kQpN], r0[kQpTasks];
-  for (int r = 0; r < kQpTasks; r++) {
-    T row[kQpN + 1];
-    for (int j = 0; j <= kQpN; j++) row[j] = dot8_dense(A[r], aleg[r], P[j]);
-    for (int a = 0; a < kNU; a++) E[r][a] = (double)row[a];
-    for (int s = 0; s < 4; s++) {
-      const double ex = (double)row[kNU + 2 * s], ez = (double)row[kNU + 2 * s + 1];
-      E[r][kNU + 2 * s] = kOscMu * ex + ez;
-      E[r][kNU + 2 * s + 1] = -kOscMu * ex + ez;
-    }
-    r0[r] = (double)e0[r] + (double)row[kQpN];
-  }
-  // ---- G = 2 E'WE + 1e-4 T'T,  g = 2 E'W r0   (OSC_RBDL.cpp:186-203)
+  // ---- E = A Mc^-1 B row by row, with Mc^-1 = M^-1 Nc (symmetric: M^-1 - M^-1 Jeq' S^+ Jeq M^-1) and
+  // B = [Bt, Jc' T]:  Z_r = Mc^-1 A_r' costs one projection + one tree-sparse solve per task; the u
+  // columns of E are then single entries of Z_r (Bt is a gear selector) and the contact columns are
+  // dots with the site Jacobians, which ARE task rows 2..9.  Neither P = Mc^-1 B nor E is stored: each
+  // row is folded into  G += 2 w e e',  g += 2 w e r0  at once (OSC_RBDL.cpp:186-203).
+  //   r0_r = Jdot qd_r - xdd*_r + A_r p0,   A_r p0 = -Z_r . bias - (JH A_r') . (S^+ JdQd)
   double G[kQpN][kQpN], g[kQpN], lo[kQpN], hi[kQpN], z[kQpN];
   for (int i = 0; i < kQpN; i++) {
-    for (int j = 0; j <= i; j++) {
-      double s = 0.0;
-      for (int r = 0; r < kQpTasks; r++) s += W[r] * E[r][i] * E[r][j];
-      G[i][j] = 2.0 * s;
-      G[j][i] = 2.0 * s;
-    }
-    double s = 0.0;
-    for (int r = 0; r < kQpTasks; r++) s += W[r] * E[r][i] * r0[r];
-    g[i] = 2.0 * s;
+    g[i] = 0.0;
+    for (int j = 0; j < kQpN; j++) G[i][j] = 0.0;
   }
+  for (int r = 0; r < kQpTasks; r++) {
+    T x[kNV], y[4];
+    expand_row(A[r], aleg[r], x);
+    CASSIE_UNROLL
+    for (int c = 0; c < 4; c++) {
+      T sacc = T(0);
+      CASSIE_UNROLL
+      for (int i = 0; i < kNV; i++) sacc += d.JH[c][i] * x[i];
+      y[c] = sacc;
+    }
+    CASSIE_UNROLL
+    for (int i = 0; i < kNV; i++) {
+      CASSIE_UNROLL
+      for (int c = 0; c < 4; c++) x[i] -= d.T1[i][c] * y[c];
+    }
+    solve(d.LD, d.Dinv, x);  // x = Z_r
+    double e[kQpN];
+    CASSIE_UNROLL
+    for (int a = 0; a < kNU; a++) {
+      T v = T(0);
+      CASSIE_UNROLL
+      for (int i = 3; i < kNV; i++)
+        if (m.act_dof[a] == i) v = x[i];
+      e[a] = (double)(m.act_gear[a] * v);
+    }
+    CASSIE_UNROLL
+    for (int s = 0; s < 4; s++) {
+      const double ex = (double)dot8_dense(A[2 + 2 * s], s / 2, x), ez = (double)dot8_dense(A[3 + 2 * s], s / 2, x);
+      e[kNU + 2 * s] = kOscMu * ex + ez;
+      e[kNU + 2 * s + 1] = -kOscMu * ex + ez;
+    }
+    T zb = T(0), ys = T(0);
+    CASSIE_UNROLL
+    for (int i = 0; i < kNV; i++) zb += x[i] * d.bias[i];
+    CASSIE_UNROLL
+    for (int c = 0; c < 4; c++) ys += y[c] * d.sjd[c];
+    const double r0 = (double)(e0[r] - zb - ys);
+    const double w2 = 2.0 * W[r];
+    for (int i = 0; i < kQpN; i++) {
+      const double wi = w2 * e[i];
+      g[i] += wi * r0;
+      for (int j = 0; j <= i; j++) G[i][j] += wi * e[j];
+    }
+  }
+  for (int i = 0; i < kQpN; i++)
+    for (int j = 0; j < i; j++) G[j][i] = G[i][j];
   for (int s = 0; s < 4; s++) {
     const int a = kNU + 2 * s, b = a + 1;
     G[a][a] += kOscWForce * (kOscMu * kOscMu + 1.0);
@@ -210,7 +224,7 @@ CASSIE_HD void osc_control(const PlanarModel<T>& m, const Kin<T>& k, const T* qd
   for (int a = 0; a < kNU; a++) { lo[a] = (double)m.act_lo[a]; hi[a] = (double)m.act_hi[a]; }
   for (int i = kNU; i < kQpN; i++) { lo[i] = 0.0; hi[i] = 1e30; }
   unsigned at_lo = qp_set ? (*qp_set & 0x3fffu) : 0u, at_hi = qp_set ? ((*qp_set >> 14) & 0x3fu) : 0u;
-  box_qp_solve(G, g, lo, hi, z, at_lo, at_hi, 60, st);
+  box_qp_solve(G, g, lo, hi, z, at_lo, at_hi, 300, st);
   if (qp_set) *qp_set = at_lo | (at_hi << 14);
   CASSIE_UNROLL
   for (int a = 0; a < kNU; a++) u[a] = (T)z[a];
