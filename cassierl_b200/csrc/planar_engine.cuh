@@ -358,6 +358,13 @@ struct Rows {
 
 constexpr double kMinVal = 1e-15;
 
+// general solimp power: out of line (powf/pow inline ~800 SASS instructions per call site, 16 k in total
+// before; every MJCF in scope uses the default power 2)
+template <typename T>
+CASSIE_COLD T impedance_pow(const T* si, T x) {
+  if (x <= si[3]) return Num<T>::pow_(x, si[4]) / Num<T>::pow_(si[3], si[4] - T(1));
+  return T(1) - Num<T>::pow_(T(1) - x, si[4]) / Num<T>::pow_(T(1) - si[3], si[4] - T(1));
+}
 template <typename T>
 CASSIE_HD T impedance(const T* si, T pos) {  // getimpedance [EXT], margin = 0
   if (si[0] == si[1] || si[2] <= T(kMinVal)) return T(0.5) * (si[0] + si[1]);
@@ -366,8 +373,8 @@ CASSIE_HD T impedance(const T* si, T pos) {  // getimpedance [EXT], margin = 0
   if (x <= T(0)) return si[0];
   T y;
   if (si[4] == T(1)) y = x;
-  else if (x <= si[3]) y = Num<T>::pow_(x, si[4]) / Num<T>::pow_(si[3], si[4] - T(1));
-  else y = T(1) - Num<T>::pow_(T(1) - x, si[4]) / Num<T>::pow_(T(1) - si[3], si[4] - T(1));
+  else if (si[4] == T(2)) y = x <= si[3] ? x * x / si[3] : T(1) - (T(1) - x) * (T(1) - x) / (T(1) - si[3]);
+  else y = impedance_pow(si, x);
   return si[0] + y * (si[1] - si[0]);
 }
 
