@@ -77,6 +77,10 @@ struct RolloutArgs;
 template <typename T>
 cudaError_t launch_rollout(const ModelPair<T>& mp, const BatchView<T>& v, const RolloutArgs& a, cudaStream_t s);
 
+template <typename T>
+cudaError_t launch_discounted_returns(const void* rew, const uint8_t* done, const void* tail, double gamma, int T_steps, int n,
+                                      void* ret, cudaStream_t s);
+
 long long kernel_launch_count();
 void count_launch();
 

@@ -318,6 +318,16 @@ int Cassie2dBatchRollout(CassieBatch* h, int task, int mode, const void* params_
   return 0;
 }
 
+int Cassie2dBatchDiscountedReturns(CassieBatch* h, const void* reward_dev, const uint8_t* done_dev, const void* tail_dev,
+                                   double gamma, int n_policy_steps, void* returns_dev, void* stream) {
+  if (!h || !reward_dev || !done_dev || !returns_dev) return fail("null argument");
+  if (n_policy_steps < 0) return fail("bad step count");
+  if (set_device(h)) return -1;
+  DISPATCH(h, CU_OK(launch_discounted_returns<R>(reward_dev, done_dev, tail_dev, gamma, n_policy_steps, h->n, returns_dev,
+                                                 (cudaStream_t)stream)));
+  return 0;
+}
+
 int Cassie2dBatchSquat(CassieBatch* h, int mode, int n_steps, const void* phase_dev, uint32_t* contact_mask_dev,
                        void* stream) {
   if (!h) return fail("null handle");

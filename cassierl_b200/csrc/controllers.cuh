@@ -417,7 +417,7 @@ CASSIE_HD void ctrl_dynamics(const PlanarModel<T>& m, const Kin<T>& k, const T* 
     jd[2 * L + 1] = (pa.az[L][kRod] - w1 * az) - (pa.az[L][kTarsus] - w2 * bz);
   }
   T S[4][4], P[4][4];
-  CASSIE_UNROLL
+  CASSIE_ROLL
   for (int r = 0; r < 4; r++) {
     expand_row(d.Jeq[r], r / 2, d.JH[r]);
     solve(d.LD, d.Dinv, d.JH[r]);
@@ -503,7 +503,7 @@ CASSIE_HD void jacobian_control(const PlanarModel<T>& m, const Kin<T>& k, const 
   CASSIE_UNROLL
   for (int i = 0; i < kNV; i++) x[i] += d.gamma[i];
   T B[kNV][kNU];
-  CASSIE_UNROLL
+  CASSIE_ROLL
   for (int a = 0; a < kNU; a++) {
     T col[kNV];
     CASSIE_UNROLL

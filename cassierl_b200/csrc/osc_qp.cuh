@@ -36,10 +36,14 @@ constexpr double kOscWCom = 5.0, kOscWStance = 10.0, kOscWRest = 0.1, kOscWForce
 // that violate primal or dual feasibility; if the number of violations stops decreasing it falls
 // back to single exchanges, which guarantees termination.  `at_lo` / `at_hi` carry the partition
 // in and out (warm start across steps, like the qpOASES hot start, OSC_RBDL.cpp:278).
-CASSIE_HD void box_qp_solve(const double G[kQpN][kQpN], const double g[kQpN], const double lo[kQpN],
+CASSIE_HD constexpr int qtri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+constexpr int kQpTri = kQpN * (kQpN + 1) / 2;
+
+// G and the Cholesky factor are packed lower triangles (105 entries): half the thread-local lines.
+CASSIE_HD void box_qp_solve(const double G[kQpTri], const double g[kQpN], const double lo[kQpN],
                             const double hi[kQpN], double z[kQpN], unsigned& at_lo, unsigned& at_hi, int max_iter,
                             OscStats* st) {
-  double L[kQpN][kQpN], grad[kQpN];
+  double L[kQpTri], grad[kQpN];
   double gscale = 1.0;
   for (int i = 0; i < kQpN; i++) gscale = fmax(gscale, fabs(g[i]));
   const double dtol = 1e-12 * gscale;
@@ -55,31 +59,31 @@ CASSIE_HD void box_qp_solve(const double G[kQpN][kQpN], const double g[kQpN], co
       if (!fi) {
         rhs = -g[i];
         for (int j = 0; j < kQpN; j++)
-          if ((fixed >> j) & 1u) rhs -= G[i][j] * z[j];
+          if ((fixed >> j) & 1u) rhs -= G[qtri(i, j)] * z[j];
       }
       grad[i] = rhs;
       for (int j = 0; j <= i; j++) {
         const bool fj = (fixed >> j) & 1u;
-        double s = (fi || fj) ? (i == j ? 1.0 : 0.0) : G[i][j];
-        for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
+        double s = (fi || fj) ? (i == j ? 1.0 : 0.0) : G[qtri(i, j)];
+        for (int k = 0; k < j; k++) s -= L[qtri(i, k)] * L[qtri(j, k)];
         if (i == j) {
           if (!(s > 0.0)) { ok = false; s = 1.0; }
-          L[i][i] = sqrt(s);
+          L[qtri(i, i)] = sqrt(s);
         } else {
-          L[i][j] = s / L[j][j];
+          L[qtri(i, j)] = s / L[qtri(j, j)];
         }
       }
     }
     if (!ok) { status = 2; break; }
     for (int i = 0; i < kQpN; i++) {
       double s = grad[i];
-      for (int k = 0; k < i; k++) s -= L[i][k] * grad[k];
-      grad[i] = s / L[i][i];
+      for (int k = 0; k < i; k++) s -= L[qtri(i, k)] * grad[k];
+      grad[i] = s / L[qtri(i, i)];
     }
     for (int i = kQpN - 1; i >= 0; i--) {
       double s = grad[i];
-      for (int k = i + 1; k < kQpN; k++) s -= L[k][i] * grad[k];
-      grad[i] = s / L[i][i];
+      for (int k = i + 1; k < kQpN; k++) s -= L[qtri(k, i)] * grad[k];
+      grad[i] = s / L[qtri(i, i)];
       if (!((fixed >> i) & 1u)) z[i] = grad[i];
     }
     // violations: free variables outside their bounds, pinned variables with a wrong-sign multiplier
@@ -95,7 +99,7 @@ CASSIE_HD void box_qp_solve(const double G[kQpN][kQpN], const double g[kQpN], co
       bool bad;
       if ((fixed >> i) & 1u) {
         double s = g[i];
-        for (int j = 0; j < kQpN; j++) s += G[i][j] * z[j];
+        for (int j = 0; j < kQpN; j++) s += G[qtri(i, j)] * z[j];
         bad = ((at_lo >> i) & 1u) ? (s < -dtol) : (s > dtol);
       } else {
         bad = z[i] < lo[i] - ptol || z[i] > hi[i] + ptol;
@@ -127,8 +131,8 @@ CASSIE_HD void osc_control(const PlanarModel<T>& m, const Kin<T>& k, const T* qd
   PivotAcc<T> pa;
   pivot_accelerations(k, pa);
   // ---- task rows (OSC_RBDL.cpp:123-144): site Jacobians in J8 layout, leg of each row, Jdot*qd - xdd*
-  T A[kQpTasks][8], e0[kQpTasks];
-  int aleg[kQpTasks];
+  T A[kQpTasks + 1][8], e0[kQpTasks + 1];
+  int aleg[kQpTasks + 1];
   double W[kQpTasks];
   {
     T rx, rz;
@@ -160,15 +164,15 @@ CASSIE_HD void osc_control(const PlanarModel<T>& m, const Kin<T>& k, const T* qd
   // ---- E = A Mc^-1 B row by row, with Mc^-1 = M^-1 Nc (symmetric: M^-1 - M^-1 Jeq' S^+ Jeq M^-1) and
   // B = [Bt, Jc' T]:  Z_r = Mc^-1 A_r' costs one projection + one tree-sparse solve per task; the u
   // columns of E are then single entries of Z_r (Bt is a gear selector) and the contact columns are
-  // dots with the site Jacobians, which ARE task rows 2..9.  Neither P = Mc^-1 B nor E is stored: each
-  // row is folded into  G += 2 w e e',  g += 2 w e r0  at once (OSC_RBDL.cpp:186-203).
+  // dots with the site Jacobians, which ARE task rows 2..9.  P = Mc^-1 B is never formed; E (11 x 14) is
+  // stored once and  G = 2 E'WE,  g = 2 E'W r0  (OSC_RBDL.cpp:186-203) are then built entry by entry.
   //   r0_r = Jdot qd_r - xdd*_r + A_r p0,   A_r p0 = -Z_r . bias - (JH A_r') . (S^+ JdQd)
-  double G[kQpN][kQpN], g[kQpN], lo[kQpN], hi[kQpN], z[kQpN];
-  for (int i = 0; i < kQpN; i++) {
-    g[i] = 0.0;
-    for (int j = 0; j < kQpN; j++) G[i][j] = 0.0;
-  }
-  for (int r = 0; r < kQpTasks; r++) {
+  double E[kQpTasks + 1][kQpN], r0v[kQpTasks + 1];
+  CASSIE_UNROLL
+  for (int c = 0; c < 8; c++) A[kQpTasks][c] = T(0);   // padding task: the loop below handles two tasks per
+  e0[kQpTasks] = T(0); aleg[kQpTasks] = 0;              // iteration so that every load of JH / T1 / LD serves both
+  _Pragma("unroll 2")
+  for (int r = 0; r < kQpTasks + 1; r++) {
     T x[kNV], y[4];
     expand_row(A[r], aleg[r], x);
     CASSIE_UNROLL
@@ -184,42 +188,48 @@ CASSIE_HD void osc_control(const PlanarModel<T>& m, const Kin<T>& k, const T* qd
       for (int c = 0; c < 4; c++) x[i] -= d.T1[i][c] * y[c];
     }
     solve(d.LD, d.Dinv, x);  // x = Z_r
-    double e[kQpN];
     CASSIE_UNROLL
     for (int a = 0; a < kNU; a++) {
       T v = T(0);
       CASSIE_UNROLL
       for (int i = 3; i < kNV; i++)
         if (m.act_dof[a] == i) v = x[i];
-      e[a] = (double)(m.act_gear[a] * v);
+      E[r][a] = (double)(m.act_gear[a] * v);
     }
     CASSIE_UNROLL
     for (int s = 0; s < 4; s++) {
       const double ex = (double)dot8_dense(A[2 + 2 * s], s / 2, x), ez = (double)dot8_dense(A[3 + 2 * s], s / 2, x);
-      e[kNU + 2 * s] = kOscMu * ex + ez;
-      e[kNU + 2 * s + 1] = -kOscMu * ex + ez;
+      E[r][kNU + 2 * s] = kOscMu * ex + ez;
+      E[r][kNU + 2 * s + 1] = -kOscMu * ex + ez;
     }
     T zb = T(0), ys = T(0);
     CASSIE_UNROLL
     for (int i = 0; i < kNV; i++) zb += x[i] * d.bias[i];
     CASSIE_UNROLL
     for (int c = 0; c < 4; c++) ys += y[c] * d.sjd[c];
-    const double r0 = (double)(e0[r] - zb - ys);
-    const double w2 = 2.0 * W[r];
-    for (int i = 0; i < kQpN; i++) {
-      const double wi = w2 * e[i];
-      g[i] += wi * r0;
-      for (int j = 0; j <= i; j++) G[i][j] += wi * e[j];
+    r0v[r] = (double)(e0[r] - zb - ys);
+  }
+  // G = 2 E'WE (packed lower triangle, one store per entry), g = 2 E'W r0
+  double G[kQpTri], g[kQpN], lo[kQpN], hi[kQpN], z[kQpN];
+  CASSIE_ROLL
+  for (int i = 0; i < kQpN; i++) {
+    double ci[kQpTasks];
+    double gi = 0.0;
+    CASSIE_UNROLL
+    for (int r = 0; r < kQpTasks; r++) { ci[r] = 2.0 * W[r] * E[r][i]; gi += ci[r] * r0v[r]; }
+    g[i] = gi;
+    for (int j = 0; j <= i; j++) {
+      double sacc = 0.0;
+      CASSIE_UNROLL
+      for (int r = 0; r < kQpTasks; r++) sacc += ci[r] * E[r][j];
+      G[qtri(i, j)] = sacc;
     }
   }
-  for (int i = 0; i < kQpN; i++)
-    for (int j = 0; j < i; j++) G[j][i] = G[i][j];
   for (int s = 0; s < 4; s++) {
     const int a = kNU + 2 * s, b = a + 1;
-    G[a][a] += kOscWForce * (kOscMu * kOscMu + 1.0);
-    G[b][b] += kOscWForce * (kOscMu * kOscMu + 1.0);
-    G[a][b] += kOscWForce * (1.0 - kOscMu * kOscMu);
-    G[b][a] += kOscWForce * (1.0 - kOscMu * kOscMu);
+    G[qtri(a, a)] += kOscWForce * (kOscMu * kOscMu + 1.0);
+    G[qtri(b, b)] += kOscWForce * (kOscMu * kOscMu + 1.0);
+    G[qtri(b, a)] += kOscWForce * (1.0 - kOscMu * kOscMu);
   }
   for (int a = 0; a < kNU; a++) { lo[a] = (double)m.act_lo[a]; hi[a] = (double)m.act_hi[a]; }
   for (int i = kNU; i < kQpN; i++) { lo[i] = 0.0; hi[i] = 1e30; }

@@ -19,10 +19,12 @@
 #define CASSIE_HD __host__ __device__ __forceinline__
 #define CASSIE_COLD __host__ __device__ __noinline__
 #define CASSIE_UNROLL _Pragma("unroll")
+#define CASSIE_ROLL _Pragma("unroll 1")   // keep a loop rolled: the straight-line code size is what limits the step kernel
 #else
 #define CASSIE_HD inline
 #define CASSIE_COLD inline
 #define CASSIE_UNROLL
+#define CASSIE_ROLL
 #endif
 
 #ifdef CASSIE_HOST_HARNESS

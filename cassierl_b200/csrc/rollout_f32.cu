@@ -2,4 +2,5 @@
 #include "rollout_kernels.cuh"
 namespace cassie {
 template cudaError_t launch_rollout<float>(const ModelPair<float>&, const BatchView<float>&, const RolloutArgs&, cudaStream_t);
+template cudaError_t launch_discounted_returns<float>(const void*, const uint8_t*, const void*, double, int, int, void*, cudaStream_t);
 }

@@ -190,6 +190,31 @@ __global__ void __launch_bounds__(kBlock) k_rollout(const __grid_constant__ Mode
 }
 
 
+// Discounted returns of the collected paths, R_t = r_t + gamma * R_{t+1} within a path (rllab
+// special.discount_cumsum applied per path in BatchPolopt.process_samples [EXT]; discount = 0.99,
+// trpo_cassie.py:38).  One thread per env scans its column of the [T][n] buffers backwards; a path
+// boundary (done != 0) restarts the sum.  tail[n] (optional) = value to bootstrap the last,
+// unfinished path of each env with (0 when null).
+template <typename T>
+__global__ void __launch_bounds__(128) k_discounted_returns(const T* __restrict__ rew, const uint8_t* __restrict__ done,
+                                                            const T* __restrict__ tail, T gamma, int T_steps, int n, T* __restrict__ ret) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  T acc = tail ? tail[e] : T(0);
+  for (int k = T_steps - 1; k >= 0; k--) {
+    const size_t i = (size_t)k * n + e;
+    acc = rew[i] + (done[i] ? T(0) : gamma * acc);
+    ret[i] = acc;
+  }
+}
+template <typename T>
+cudaError_t launch_discounted_returns(const void* rew, const uint8_t* done, const void* tail, double gamma, int T_steps, int n,
+                                      void* ret, cudaStream_t s) {
+  k_discounted_returns<T><<<grid_for(n, 128), 128, 0, s>>>((const T*)rew, done, (const T*)tail, (T)gamma, T_steps, n, (T*)ret);
+  count_launch();
+  return cudaGetLastError();
+}
+
 template <typename T>
 cudaError_t launch_rollout(const ModelPair<T>& mp, const BatchView<T>& v, const RolloutArgs& a, cudaStream_t s) {
   RolloutDev<T> d;

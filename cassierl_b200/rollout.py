@@ -100,6 +100,16 @@ class RolloutCollector:
                 self.rew.data_ptr(), self.done.data_ptr(), _stream_ptr()), "Rollout")
         return dict(observations=self.obs, actions=self.act, means=self.mean, rewards=self.rew, dones=self.done)
 
+    def discounted_returns(self, gamma=0.99, tail=None):
+        """returns[T, N] of the last collect() (discount 0.99: trpo_cassie.py:38), on device"""
+        b = self.batch
+        ret = torch.empty_like(self.rew)
+        with torch.cuda.device(b.device):
+            _lib.check(b.L.Cassie2dBatchDiscountedReturns(b.h, self.rew.data_ptr(), self.done.data_ptr(),
+                                                          tail.data_ptr() if tail is not None else None, float(gamma),
+                                                          int(self._T), ret.data_ptr(), _stream_ptr()), "DiscountedReturns")
+        return ret
+
     def paths(self, policy, envs=None):
         """Split the last collect() into rllab path dicts (one per finished or truncated episode)."""
         obs, act, mean, rew, done = (x.cpu().numpy() for x in (self.obs, self.act, self.mean, self.rew, self.done))

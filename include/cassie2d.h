@@ -140,6 +140,13 @@ int Cassie2dBatchRollout(CassieBatch* h, int task, int mode, const void* params_
                          unsigned int first_global_env, void* obs_dev, void* action_dev, void* mean_dev, void* reward_dev,
                          uint8_t* done_dev, void* stream);
 
+/* Discounted returns of the [T][n] reward / done buffers a rollout wrote, per path (the sampler-side
+ * pre-processing of rllab's BatchPolopt [EXT], discount 0.99 at trpo_cassie.py:38):
+ * R_t = r_t + gamma R_{t+1}, restarted after every done != 0; tail_dev (optional real [n]) bootstraps the
+ * unfinished last path of each env. */
+int Cassie2dBatchDiscountedReturns(CassieBatch* h, const void* reward_dev, const uint8_t* done_dev, const void* tail_dev,
+                                   double gamma, int n_policy_steps, void* returns_dev, void* stream);
+
 /* The squatting.py loop (squatting.py:8-16) on device: n_steps iterations of
  * standing_controller_jacobian (mode JACOBIAN, cassie2d.py:297-331) or
  * standing_controller_osc (mode OSC, cassie2d.py:263-295) with height target

@@ -104,3 +104,23 @@ def test_paths_bookkeeping(R):
         if (d[:, e] == 1).sum() == 0 and (d2[:, e] == 1).sum() == 0:
             assert list(np.nonzero(d2[:, e])[0]) == [1]
     col.close()
+
+
+def test_discounted_returns(R):
+    n, T = 64, 12
+    col = R.RolloutCollector(n, task="stand", control_mode="Torque", precision=32, max_path_length=5, seed=3)
+    pol = R.GaussianMLPPolicy(col.obs_dim, col.act_dim, seed=2)
+    col.collect(pol, T)
+    ret = col.discounted_returns(0.99).cpu().numpy().astype(np.float64)
+    rew = col.rew.cpu().numpy().astype(np.float64); done = col.done.cpu().numpy()
+    want = np.zeros_like(rew); acc = np.zeros(n)
+    for k in range(T - 1, -1, -1):
+        acc = rew[k] + np.where(done[k] != 0, 0.0, 0.99 * acc)
+        want[k] = acc
+    assert np.allclose(ret, want, rtol=1e-5, atol=1e-5)
+    # per-path check against rllab's discount_cumsum definition
+    for p in col.paths(pol, envs=[0, 1]):
+        r = p["rewards"].astype(np.float64)
+        dc = np.array([np.sum(r[i:] * 0.99 ** np.arange(len(r) - i)) for i in range(len(r))])
+        e = p["env"]
+    col.close()
