@@ -247,7 +247,7 @@ CASSIE_COLD void pinv13x6_apply_jacobi(T B[kNV][kNU], T tol, const T rhs[kNV], T
 template <typename T>
 CASSIE_HD void sym4_pinv(T A[4][4], T tol, T P[4][4]) {
   // Cholesky A = L L^T, P = L^-T L^-1
-  T L[4][4], Li[4][4];
+  T L[4][4], Li[4][4], invd[4];
   bool ok = true;
   CASSIE_UNROLL
   for (int i = 0; i < 4; i++) {
@@ -261,8 +261,9 @@ CASSIE_HD void sym4_pinv(T A[4][4], T tol, T P[4][4]) {
         if (i == j) {
           ok = ok && (sacc > T(0));
           L[i][i] = Num<T>::sqrt_(sacc > T(0) ? sacc : T(1));
+          invd[i] = T(1) / L[i][i];
         } else {
-          L[i][j] = sacc / L[j][j];
+          L[i][j] = sacc * invd[j];
         }
       }
     }
@@ -278,7 +279,7 @@ CASSIE_HD void sym4_pinv(T A[4][4], T tol, T P[4][4]) {
         CASSIE_UNROLL
         for (int k = 0; k < 4; k++)
           if (k >= j && k < i) sacc -= L[i][k] * Li[k][j];
-        Li[i][j] = sacc / L[i][i];
+        Li[i][j] = sacc * invd[i];
       }
     }
   }
@@ -301,7 +302,7 @@ CASSIE_HD void sym4_pinv(T A[4][4], T tol, T P[4][4]) {
 template <typename T>
 CASSIE_HD void pinv13x6_apply(T B[kNV][kNU], T tol, const T rhs[kNV], T u[kNU]) {
   // modified Gram-Schmidt QR, B = Q R (Q overwrites a copy of B)
-  T Q[kNV][kNU], R[kNU][kNU], y[kNU];
+  T Q[kNV][kNU], R[kNU][kNU], y[kNU], rinv[kNU];
   CASSIE_UNROLL
   for (int i = 0; i < kNV; i++) {
     CASSIE_UNROLL
@@ -316,6 +317,7 @@ CASSIE_HD void pinv13x6_apply(T B[kNV][kNU], T tol, const T rhs[kNV], T u[kNU]) 
     ok = ok && (nn > T(1e-30));
     const T rjj = Num<T>::sqrt_(nn > T(1e-30) ? nn : T(1));
     const T inv = T(1) / rjj;
+    rinv[j] = inv;
     R[j][j] = rjj;
     T d = T(0);
     CASSIE_UNROLL
@@ -345,7 +347,7 @@ CASSIE_HD void pinv13x6_apply(T B[kNV][kNU], T tol, const T rhs[kNV], T u[kNU]) 
         CASSIE_UNROLL
         for (int k = 0; k < kNU; k++)
           if (k > i && k <= j) sacc -= R[i][k] * Ri[k][j];
-        Ri[i][j] = sacc / R[i][i];
+        Ri[i][j] = sacc * rinv[i];
       }
       fro += Ri[i][j] * Ri[i][j];
     }
