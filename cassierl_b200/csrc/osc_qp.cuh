@@ -227,20 +227,32 @@ CASSIE_HD void osc_control(const PlanarModel<T>& m, const Kin<T>& k, const T* qd
     for (int c = 0; c < 4; c++) ys += y[c] * d.sjd[c];
     r0v[r] = (double)(e0[r] - zb - ys);
   }
-  // G = 2 E'WE (packed lower triangle, one store per entry), g = 2 E'W r0
+  // G = 2 E'WE (packed lower triangle, one store per entry), g = 2 E'W r0.  Two rows of G per pass: the
+  // weighted columns i, i+1 of E sit in registers, every column j <= i+1 is loaded once and feeds four
+  // independent accumulation chains.
   double G[kQpTri], g[kQpN], lo[kQpN], hi[kQpN], z[kQpN];
   CASSIE_ROLL
-  for (int i = 0; i < kQpN; i++) {
-    double ci[kQpTasks];
-    double gi = 0.0;
+  for (int i = 0; i < kQpN; i += 2) {
+    double c0[kQpTasks], c1[kQpTasks];
+    double g0 = 0.0, g1 = 0.0;
     CASSIE_UNROLL
-    for (int r = 0; r < kQpTasks; r++) { ci[r] = 2.0 * W[r] * E[r][i]; gi += ci[r] * r0v[r]; }
-    g[i] = gi;
-    for (int j = 0; j <= i; j++) {
-      double sacc = 0.0;
+    for (int r = 0; r < kQpTasks; r++) {
+      const double w2 = 2.0 * W[r];
+      c0[r] = w2 * E[r][i]; c1[r] = w2 * E[r][i + 1];
+      g0 += c0[r] * r0v[r]; g1 += c1[r] * r0v[r];
+    }
+    g[i] = g0; g[i + 1] = g1;
+    CASSIE_ROLL
+    for (int j = 0; j <= i + 1; j++) {
+      double s0a = 0.0, s0b = 0.0, s1a = 0.0, s1b = 0.0;
       CASSIE_UNROLL
-      for (int r = 0; r < kQpTasks; r++) sacc += ci[r] * E[r][j];
-      G[qtri(i, j)] = sacc;
+      for (int r = 0; r < kQpTasks; r++) {
+        const double ej = E[r][j];
+        if (r & 1) { s0b += c0[r] * ej; s1b += c1[r] * ej; }
+        else { s0a += c0[r] * ej; s1a += c1[r] * ej; }
+      }
+      if (j <= i) G[qtri(i, j)] = s0a + s0b;
+      G[qtri(i + 1, j)] = s1a + s1b;
     }
   }
   for (int s = 0; s < 4; s++) {
