@@ -35,7 +35,7 @@ if ROOT not in sys.path:
 # Mean over the first 100 steps of the squatting stream at four phases (9.5-11 constraint rows, PGS at
 # its 50-sweep cap); the fast path's inert padding rows are NOT counted.  torque_random / pd_env use
 # the torque / PD step figures of the same stream (their own streams visit more contact states).
-FLOPS_PER_STEP = {"squat_osc": 48.7e3, "squat_jacobian": 47.6e3, "torque_random": 24.2e3, "pd_env": 22.6e3}
+FLOPS_PER_STEP = {"squat_osc": 43.3e3, "squat_jacobian": 30.5e3, "torque_random": 24.1e3, "pd_env": 22.5e3}
 # Algorithmic HBM bytes of one launch per env: qpos, qvel, warm start read + written (13 reals each),
 # lagged op-space state 12 r/w, clock 8 r/w, stats 16 w, + per-workload action/phase/obs traffic.
 STATE_BYTES_PER_ENV_F32 = 2 * (39 * 4 + 12 * 4 + 8) + 16
