@@ -191,7 +191,9 @@ def run_native(args):
     dt_t = torch.float64 if args.precision == 64 else torch.float32
     rs = 8 if args.precision == 64 else 4
     gid0 = rank * n                                   # global env ids: results independent of the GPU count
-    phase = (2 * np.pi * (gid0 + np.arange(n)) / (n * world)).astype(np.float64)
+    # every block of `n` consecutive global ids spans one full period of the squat target, so each rank
+    # carries the same mix of phases (load balance) and rank r's envs do not depend on the GPU count
+    phase = (2 * np.pi * ((gid0 + np.arange(n)) % n) / n).astype(np.float64)
     gen = np.random.default_rng(1 + rank)
     hi = np.array([12.0, 12.0, 0.9, 12.0, 12.0, 0.9])
     total_steps = args.warmup + args.steps
