@@ -299,6 +299,11 @@ def run_native(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        traffic = None                                         # DRAM bytes per launch from the last ncu --set full capture
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
         fp32_peak = L.CassieMeasureFp32Peak(local)            # TFLOP/s, measured live on this GPU
         fl = FLOPS_PER_STEP.get(wl) or 0.0
         flops_launch = fl * n * sub
@@ -314,7 +319,7 @@ def run_native(args):
                        "policy_steps_per_s": value / sub, "l2": "flushed between timed steps (256 MiB memset)",
                        "parallelism": "env-sharded dp%d, no data-path collective" % world},
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp32_peak if fp32_peak > 0 else None, "traffic": None,
+                         "frac": achieved / fp32_peak if fp32_peak > 0 else None, "traffic": traffic,
                          "peak_source": "measured live: register-only FFMA kernel (CassieMeasureFp32Peak); MEASURED_PEAKS.json has no FP32 figure",
                          "flops_per_env_step": fl, "kernel_ms": ms_launch,
                          "hbm": {"achieved_gbs": bytes_launch / (ms_launch * 1e-3) / 1e9, "peak_gbs": hbm_peak,

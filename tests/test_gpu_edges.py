@@ -67,11 +67,11 @@ def test_zero_substeps_and_masked_reset(E, LIB, oracle):
 
 
 def test_cold_path_fp32_single_step(E, LIB, oracle, omodel):
-    """States with violated joint limits and thigh / shin / pelvis floor contacts (robots that fell under
+    """States with violated joint limits and tarsus / shin floor contacts (robots thrown around by
     random torques): the out-of-line general constraint path in fp32, teacher-forced, 1e-5."""
     n = 24
     rng = np.random.default_rng(77)
-    pres = []; refs = []; acts = []; rmask = []; nrows = []
+    pres = []; refs = []; acts = []; rmask = []; n_rare = 0
     for e in range(n):
         d = oracle.Data(omodel); d.set_state(QPOS_INIT_CTOR, np.zeros(13))
         U = rng.uniform(-1, 1, (80, 6)) * TORQUE_HIGH
@@ -80,10 +80,12 @@ def test_cold_path_fp32_single_step(E, LIB, oracle, omodel):
         (q, v), w = d.state(), d.warmstart()
         a = U[(500 + 10 * e) // 10]
         d.step(a)
+        ef = d.efc(); geoms = d.contacts()["geom"]           # geoms 5 / 9 are the toe capsules
+        n_rare += bool((ef["type"] == 1).any() or any(g not in (5, 9) for g in geoms))
         q1, v1 = d.state()
         pres.append((s26(oracle, q, v), w)); refs.append(np.concatenate([q1, v1])); acts.append(a)
-        rmask.append(d.contact_mask()); nrows.append(len(d.efc()["pos"]))
-    assert max(nrows) > 18                                   # beyond 4 connect + 4 toe contacts (3-D rows)
+        rmask.append(d.contact_mask())
+    assert n_rare >= 8                                       # joint-limit rows and / or tarsus, shin, thigh contacts
     b = E.Cassie2dBatch(n, precision=32)
     b.reset(torch.tensor(np.array([p[0] for p in pres]), dtype=torch.float32, device=b.device))
     b.set_warm_start(torch.tensor(np.array([p[1] for p in pres])))
@@ -97,7 +99,7 @@ def test_cold_path_fp32_single_step(E, LIB, oracle, omodel):
     assert np.median(err.max(axis=1)) < 1e-5
     assert np.array_equal(mask.cpu().numpy().astype(np.uint64), np.array(rmask, np.uint64))
     st = b.stats().cpu().numpy()
-    assert st[:, 0].max() > 12 and (st[:, 1] <= 50).all()
+    assert (st[:, 0] >= 4).all() and (st[:, 1] <= 50).all()
     b.close()
 
 

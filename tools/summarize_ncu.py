@@ -46,5 +46,20 @@ def main(rep):
     print("opcode mix:", ", ".join("%s %.1f%%" % (o, 100 * n / total) for o, n in byop.most_common(12)))
 
 
+def dram_bytes(rep):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the captured launch, in bytes"""
+    raw = list(csv.reader(io.StringIO(ncu(rep, "raw"))))
+    hdr, units, vals = raw[0], raw[1], raw[-1]
+    tot = 0.0
+    for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        i = hdr.index(k)
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+        tot += float(vals[i].replace(",", "")) * scale
+    return tot
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if len(sys.argv) > 2 and sys.argv[2] == "--traffic":
+        print(int(dram_bytes(sys.argv[1])))
+    else:
+        main(sys.argv[1])
