@@ -8,7 +8,17 @@
 
 namespace cassie {
 
-constexpr int kBlock = 32;
+#ifndef CASSIE_BLOCK
+#define CASSIE_BLOCK 32
+#endif
+constexpr int kBlock = CASSIE_BLOCK;
+// With several warps per CTA, a barrier per simulator step keeps them in lock step so that they share
+// instruction-cache fills (instruction fetch is the top stall of the step kernels).
+__device__ __forceinline__ void step_barrier() {
+#if CASSIE_BLOCK > 32
+  __syncthreads();
+#endif
+}
 
 // controller model of a mode: OSC runs in double in every build, the other modes in T
 template <int MODE, typename T>
@@ -140,8 +150,9 @@ __device__ __forceinline__ void write_obs(const BatchView<T>& v, int task, int e
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kBlock) k_env_step(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v,
                                                       const __grid_constant__ EnvStepDev<T> a) {
-  const int e = blockIdx.x * kBlock + threadIdx.x;
-  if (e >= v.n) return;
+  const int e_raw = blockIdx.x * kBlock + threadIdx.x;
+  const bool active = e_raw < v.n;   // inactive lanes shadow the last env (they must reach the barriers)
+  const int e = active ? e_raw : v.n - 1;
   T q[kNV], qd[kNV], w[kNV], act[7], u[kNU];
   load_env(v, e, q, qd, w);
   constexpr int adim = action_dim(MODE);
@@ -155,9 +166,11 @@ __global__ void __launch_bounds__(kBlock) k_env_step(const __grid_constant__ Mod
   double t = v.clock[e];
   unsigned qps = v.qp_set[e];
   for (int s = 0; s < a.n_sub; s++) {
+    step_barrier();
     controller_step<MODE>(mp.phys, mp.phys_d, ctrl_model<MODE>(mp), mp.ctrl_d, q, qd, w, act, rows, u, s == a.n_sub - 1 ? &op : nullptr, &st, &qs, &qps);
     t += 0.0005;  // cassie2d.py:122
   }
+  if (!active) return;
   T o18[18], ref9[9], r;
   int done;
   op_state_array(op, q, qd, o18);
@@ -226,8 +239,9 @@ __global__ void __launch_bounds__(128) k_env_reset(const __grid_constant__ Model
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kBlock) k_squat(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v,
                                                    const T* __restrict__ phase, int n_steps, uint32_t* mask) {
-  const int e = blockIdx.x * kBlock + threadIdx.x;
-  if (e >= v.n) return;
+  const int e_raw = blockIdx.x * kBlock + threadIdx.x;
+  const bool active = e_raw < v.n;   // inactive lanes shadow the last env (they must reach the barriers)
+  const int e = active ? e_raw : v.n - 1;
   T q[kNV], qd[kNV], w[kNV], act[7], u[kNU];
   load_env(v, e, q, qd, w);
   Rows<T> rows;
@@ -240,6 +254,7 @@ __global__ void __launch_bounds__(kBlock) k_squat(const __grid_constant__ ModelP
   const double wq = 0.5 * 3.1415;  // squatting.py:9
   unsigned qps = v.qp_set[e];
   for (int s = 0; s < n_steps; s++) {
+    step_barrier();
     T o18[18];
     op_state_array(op, q, qd, o18);
     double sn, cs;
@@ -250,6 +265,7 @@ __global__ void __launch_bounds__(kBlock) k_squat(const __grid_constant__ ModelP
     controller_step<MODE>(mp.phys, mp.phys_d, ctrl_model<MODE>(mp), mp.ctrl_d, q, qd, w, act, rows, u, &op, &st, &qs, &qps);
     t = t + 0.0005;  // squatting.py:15
   }
+  if (!active) return;
   v.clock[e] = t;
   v.qp_set[e] = qps;
   store_env(v, e, q, qd, w);
