@@ -9,7 +9,7 @@
 namespace cassie {
 
 #ifndef CASSIE_BLOCK
-#define CASSIE_BLOCK 32
+#define CASSIE_BLOCK 64
 #endif
 constexpr int kBlock = CASSIE_BLOCK;
 // With several warps per CTA, a barrier per simulator step keeps them in lock step so that they share

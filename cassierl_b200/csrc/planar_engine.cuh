@@ -748,19 +748,33 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
     r.R[i] = T(1);
     r.b[i] = T(0);
   }
+  // Assembly in a ROLLED row loop (J rows read from, A written to thread-local memory with run-time
+  // indices), then A / b / jar are pulled into registers with static indices for the sweeps.  Unrolled,
+  // this block was 5 k straight-line instructions that ran ~3x slower per instruction than loop code:
+  // instruction fetch stalls at every 128-byte line (profiles/r1m_squat_osc_final.txt).
+  CASSIE_ROLL
+  for (int i = 0; i < NR; i++) {
+    T J8[8], Bi[kNV];
+    CASSIE_UNROLL
+    for (int c = 0; c < 8; c++) J8[c] = r.J[i][c];
+    const int leg = r.leg[i];
+    expand_row(J8, leg, Bi);
+    const T maref = r.b[i];
+    r.b[i] = maref + dot8_dense(J8, leg, qs);
+    r.f[i] = maref + dot8_dense(J8, leg, warm);   // jar, parked in f until the warm start below
+    if (i < 4 || i < n) solve(LD, Dinv, Bi);
+    CASSIE_ROLL
+    for (int j = 0; j <= i; j++) r.A[i][j] = dot8_dense(r.J[j], r.leg[j], Bi);
+    r.A[i][i] += r.R[i];
+  }
   T A[NR * (NR + 1) / 2], b[NR], f[NR], jar[NR];
   CASSIE_UNROLL
   for (int i = 0; i < NR; i++) {
-    T Bi[kNV];
-    expand_row(r.J[i], r.leg[i], Bi);
-    const T maref = r.b[i];
-    b[i] = maref + dot8_dense(r.J[i], r.leg[i], qs);
-    jar[i] = maref + dot8_dense(r.J[i], r.leg[i], warm);
-    if (i < 4 || i < n) solve(LD, Dinv, Bi);
+    b[i] = r.b[i];
+    jar[i] = r.f[i];
     CASSIE_UNROLL
     for (int j = 0; j < NR; j++)
-      if (j <= i) A[tri(i, j)] = dot8_dense(r.J[j], r.leg[j], Bi);
-    A[tri(i, i)] += r.R[i];
+      if (j <= i) A[tri(i, j)] = r.A[i][j];
   }
   // warm start (mj_constraintUpdate [EXT] on jar = J qacc_warmstart - aref)
   CASSIE_UNROLL
