@@ -736,11 +736,30 @@ CASSIE_HD int constraint_solve_general(const PlanarModel<T>& m, Rows<T>& r, cons
 constexpr int kFastRows = 12;
 CASSIE_HD constexpr int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 
-template <int NC, typename T>
+// NS scalar rows (4 connect rows + NS - 4 joint-limit slots, the latter clamped at f >= 0) followed by NC
+// contact pairs.  nlimit = joint-limit rows actually present (<= NS - 4).
+template <int NS, int NC, typename T>
 CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T LD[kNV][kNV], const T Dinv[kNV],
-                                    const T qs[kNV], const T warm[kNV], T fc[kNV]) {
-  constexpr int NR = 4 + 2 * NC;  // rows handled by this instantiation (NC contact pairs)
-  const int n = r.n;
+                                    const T qs[kNV], const T warm[kNV], T fc[kNV], int nlimit = 0) {
+  constexpr int NR = NS + 2 * NC;  // rows handled by this instantiation
+  int n = r.n;
+  if (NS > 4 && nlimit < NS - 4) {
+    // move the contact rows up so that they start at slot NS; the freed limit slots become inert rows
+    const int shift = NS - 4 - nlimit;
+    for (int i = n - 1; i >= 4 + nlimit; i--) {
+      CASSIE_UNROLL
+      for (int c = 0; c < 8; c++) r.J[i + shift][c] = r.J[i][c];
+      r.leg[i + shift] = r.leg[i]; r.type[i + shift] = r.type[i];
+      r.R[i + shift] = r.R[i]; r.b[i + shift] = r.b[i];
+    }
+    for (int i = 4 + nlimit; i < NS; i++) {
+      CASSIE_UNROLL
+      for (int c = 0; c < 8; c++) r.J[i][c] = T(0);
+      r.leg[i] = 0; r.type[i] = kRowLimit;
+      r.R[i] = T(1); r.b[i] = T(0);
+    }
+    n += shift;
+  }
   for (int i = n; i < NR; i++) {  // inert padding
     CASSIE_UNROLL
     for (int c = 0; c < 8; c++) r.J[i][c] = T(0);
@@ -762,7 +781,7 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
     const T maref = r.b[i];
     r.b[i] = maref + dot8_dense(J8, leg, qs);
     r.f[i] = maref + dot8_dense(J8, leg, warm);   // jar, parked in f until the warm start below
-    if (i < 4 || i < n) solve(LD, Dinv, Bi);
+    if (i < n) solve(LD, Dinv, Bi);
     CASSIE_ROLL
     for (int j = 0; j <= i; j++) r.A[i][j] = dot8_dense(r.J[j], r.leg[j], Bi);
     r.A[i][i] += r.R[i];
@@ -778,11 +797,14 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
   }
   // warm start (mj_constraintUpdate [EXT] on jar = J qacc_warmstart - aref)
   CASSIE_UNROLL
-  for (int i = 0; i < 4; i++) f[i] = -jar[i] / r.R[i];
+  for (int i = 0; i < NS; i++) {
+    const T fw = -jar[i] / r.R[i];
+    f[i] = (i >= 4 && !(jar[i] < T(0))) ? T(0) : fw;   // limit rows: force only when violated
+  }
   {
     const T mu = m.con_mu / Num<T>::sqrt_(m.impratio);
     CASSIE_UNROLL
-    for (int i = 4; i < NR; i += 2) {
+    for (int i = NS; i < NR; i += 2) {
       const T N = jar[i] * mu, U1 = jar[i + 1] * m.con_mu, Tn = Num<T>::abs_(U1);
       const T D0 = T(1) / r.R[i], D1 = T(1) / r.R[i + 1];
       T f0, f1;
@@ -836,26 +858,28 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
     T rden[NC > 0 ? NC : 1];
     CASSIE_UNROLL
     for (int p = 0; p < NC; p++) {
-      const int i = 4 + 2 * p;
+      const int i = NS + 2 * p;
       const T o0 = f[i], o1 = f[i + 1];
       const T denom = o0 * (A[tri(i, i)] * o0 + A[tri(i + 1, i)] * o1) + o1 * (A[tri(i + 1, i)] * o0 + A[tri(i + 1, i + 1)] * o1);
       rden[p] = denom >= T(kMinVal) ? T(1) / denom : T(0);
     }
     T improvement = T(0);
     CASSIE_UNROLL
-    for (int i = 0; i < 4; i++) {  // equality rows: unbounded
+    for (int i = 0; i < NS; i++) {  // scalar rows: connects unbounded, joint limits f >= 0
       T lo = T(0);
       CASSIE_UNROLL
       for (int c = 0; c < NR; c++)
         if (c < i) lo += A[tri(i, c)] * f[c];
       const T res = hi[i] + lo;
-      const T d = -res * inv[i];
-      f[i] += d;
+      T fn = f[i] - res * inv[i];
+      if (i >= 4) fn = fn < T(0) ? T(0) : fn;
+      const T d = fn - f[i];
+      f[i] = fn;
       improvement -= T(0.5) * d * d * A[tri(i, i)] + d * res;
     }
     CASSIE_UNROLL
     for (int p = 0; p < NC; p++) {  // elliptic contact: normal + one tangent
-      const int i = 4 + 2 * p;
+      const int i = NS + 2 * p;
       T lo0 = T(0), lo1 = T(0);
       CASSIE_UNROLL
       for (int c = 0; c < NR; c++)
@@ -928,7 +952,16 @@ CASSIE_COLD void constraints_cold(const PlanarModel<T>& m, const Kin<T>& k, cons
                                   int* sweeps, unsigned int* mask) {
   int nlimit = 0;
   *mask = make_rows<true>(m, k, cp, q, qd, r, &nlimit);
-  *sweeps = constraint_solve_general(m, r, LD, Dinv, qs, warm, fc);
+  // middle tier: up to 4 violated joint limits and up to 4 floor contacts of any geom still fit the
+  // register solver (robots thrown around by random actions live here); everything else is general
+#ifdef CASSIE_HOST_HARNESS
+  const bool fast_ok = !cassie_force_general_path;
+#else
+  const bool fast_ok = true;
+#endif
+  const int ncontact = (r.n - 4 - nlimit) / 2;
+  if (fast_ok && nlimit <= 4 && ncontact <= 4) *sweeps = constraint_solve_fast<8, 4>(m, r, LD, Dinv, qs, warm, fc, nlimit);
+  else *sweeps = constraint_solve_general(m, r, LD, Dinv, qs, warm, fc);
 }
 
 // One mj_step [EXT] (Cassie2d.cpp:92): forward dynamics, constraint solve, semi-implicit Euler
@@ -993,8 +1026,8 @@ CASSIE_HD void physics_step(const PlanarModel<T>& m, const PlanarModel<TG>& mg, 
 #else
     const bool wide = r.n > 8;
 #endif
-    if (wide) sweeps = constraint_solve_fast<4>(m, r, LD, Dinv, qs, warm, fc);
-    else sweeps = constraint_solve_fast<2>(m, r, LD, Dinv, qs, warm, fc);
+    if (wide) sweeps = constraint_solve_fast<4, 4>(m, r, LD, Dinv, qs, warm, fc);
+    else sweeps = constraint_solve_fast<4, 2>(m, r, LD, Dinv, qs, warm, fc);
   } else {
     constraints_cold(m, k, cp, q, qd, r, LD, Dinv, qs, warm, fc, &sweeps, &mask);
   }
