@@ -355,3 +355,75 @@ def test_host_variant_equals_device_variant(E, LIB):
     b2.step_host(LIB.MODE_TORQUE, ah, 10, out)
     assert torch.equal(s1, out)
     b1.close(); b2.close()
+
+
+# ----------------------------------------------------------------------------- BASELINE configs at full size
+def test_config1_legacy_abi_1000_step_squat(LIB, oracle, omodel):
+    """BASELINE configs[0]: single env, 1000-step squatting rollout -- here through the drop-in legacy
+    ABI (StepJacobian + GetOperationalSpaceState per step, exactly squatting.py's loop) vs the oracle."""
+    from cassierl_b200 import structs as S
+    L = LIB.load()
+    h = L.Cassie2dInit()
+    c = oracle.Cassie2d(omodel)
+    xs = S.StateOperationalSpace(); qs = S.StateGeneral(); cv = S.InterfaceStructConverter()
+    t = 0.0
+    for k in range(1000):
+        L.GetOperationalSpaceState(h, ct.byref(xs))
+        f = squat_jacobian_action(cv.operational_state_to_array(xs), t)
+        act = S.ControllerForce()
+        for i in range(3):
+            act.left_force[i] = f[i]; act.right_force[i] = f[3 + i]
+        L.StepJacobian(h, ct.byref(act))
+        c.step_jacobian(squat_jacobian_action(c.op_state(), t))
+        t = t + 0.0005
+    L.GetGeneralState(h, ct.byref(qs))
+    assert rel_err(cv.general_state_to_array(qs), c.general_state()) < 1e-7
+    assert 0.6 < qs.base_pos[1] < 1.0   # still squatting, not fallen
+
+
+def test_config2_4096_envs_random_torques_subset_vs_oracle(E, LIB, oracle, omodel):
+    """BASELINE configs[1]: 4096 envs, uniform-random torques held 10 sim steps, 1000 sim steps; a fixed
+    subset of envs is checked against the oracle (fp64 build: 1e-8 after 1000 steps, contact masks step
+    for step at the policy rate); the whole batch must stay finite."""
+    n, n_act, hold = 4096, 100, 10
+    subset = [0, 1, 2, 31, 32, 33, 1000, 2047, 2048, 4095]
+    rng = np.random.default_rng(1)
+    U = (rng.uniform(-1, 1, (n_act, n, 6)) * TORQUE_HIGH)
+    b = E.Cassie2dBatch(n, precision=64)
+    mask = torch.zeros(n, dtype=torch.int32, device=b.device)
+    Ud = torch.tensor(U, device=b.device)
+    gm = []
+    for k in range(n_act):
+        b.step_torque(Ud[k], hold, contact_mask=mask)
+        gm.append(mask[subset].cpu().numpy().copy())
+    got = b.get_general_state().cpu().numpy()
+    assert np.isfinite(got).all()
+    gm = np.array(gm)
+    for i, e in enumerate(subset):
+        ref, masks, _ = oracle_rollout_torque(oracle, omodel, U[:, e], hold)
+        q, v = q_from_s26(got[e])
+        assert rel_err(np.concatenate([q, v]), ref[-1]) < 1e-8, e
+        assert np.array_equal(gm[:, i].astype(np.uint64), masks[hold - 1::hold]), e
+    b.close()
+
+
+def test_config3_16384_envs_osc_invariants(E, LIB):
+    """BASELINE configs[2] (the bench workload): 16384 envs with the OSC squatting controller in the loop.
+    Size-independent properties: identical envs stay bitwise identical, an env's result does not depend
+    on its position in the batch, every QP reports optimality, nobody falls."""
+    n = 16384
+    b = E.Cassie2dBatch(n, precision=32)
+    b.squat(LIB.MODE_OSC, 30)
+    s = b.get_general_state()
+    assert torch.isfinite(s).all() and (s == s[0:1]).all()
+    phase = torch.linspace(0, 6.28, n, device=b.device)
+    b2 = E.Cassie2dBatch(n, precision=32); b3 = E.Cassie2dBatch(n, precision=32)
+    b2.squat(LIB.MODE_OSC, 30, phase=phase)
+    b3.squat(LIB.MODE_OSC, 30, phase=phase.flip(0))
+    s2, s3 = b2.get_general_state(), b3.get_general_state()
+    assert torch.equal(s2, s3.flip(0))
+    st = b2.stats()
+    assert (st[:, 3] == 0).all() and (st[:, 2] >= 1).all()
+    assert (s2[:, 1] > 0.6).all()
+    for x in (b, b2, b3):
+        x.close()
