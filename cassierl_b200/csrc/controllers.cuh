@@ -517,17 +517,4 @@ CASSIE_HD void jacobian_control(const PlanarModel<T>& m, const Kin<T>& k, const 
   pinv13x6_apply(B, T(1e-4), x, u);
 }
 
-// Cassie2d::StepPd control law (Cassie2d.cpp:96-112): gains are in ctrl units
-template <typename T>
-CASSIE_HD void pd_control(const PlanarModel<T>& m, const T* q, const T* qd, const T ang[kNU], T u[kNU]) {
-  CASSIE_UNROLL
-  for (int a = 0; a < kNU; a++) {
-    T qj = T(0), vj = T(0);
-    CASSIE_UNROLL
-    for (int i = 3; i < kNV; i++)
-      if (m.act_dof[a] == i) { qj = q[i]; vj = qd[i]; }
-    u[a] = T(10) * (ang[a] - qj) + T(5) * (T(0) - vj);
-  }
-}
-
 }  // namespace cassie

@@ -1,7 +1,8 @@
 // CUDA kernels of the batched Cassie2d engine: one env per thread, env state in registers for
-// the whole launch (all substeps fused), constraint rows in thread-local memory (L1-resident),
-// model constants in the kernel-parameter constant bank (warp-uniform reads).
-// DESIGN.md section 4 has the mapping rationale and the measured alternatives.
+// the whole launch (all substeps fused), constraint rows staged in thread-local memory and the
+// constraint system (A, b, f) in registers for the PGS sweeps, model constants in the kernel-parameter
+// constant bank (warp-uniform reads), 64-thread CTAs kept in lock step by one barrier per sim step.
+// DESIGN.md sections 4-5 have the mapping rationale and the measured optimisation log.
 #pragma once
 #include "batch_state.h"
 #include "cassie_step.cuh"
