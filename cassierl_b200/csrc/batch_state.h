@@ -81,6 +81,12 @@ template <typename T>
 cudaError_t launch_discounted_returns(const void* rew, const uint8_t* done, const void* tail, double gamma, int T_steps, int n,
                                       void* ret, cudaStream_t s);
 
+struct BaselineArgs;
+template <typename T>
+cudaError_t launch_baseline_moments(const BaselineArgs& a, cudaStream_t s);
+template <typename T>
+cudaError_t launch_advantages(const BaselineArgs& a, cudaStream_t s);
+
 long long kernel_launch_count();
 void count_launch();
 

@@ -328,6 +328,33 @@ int Cassie2dBatchDiscountedReturns(CassieBatch* h, const void* reward_dev, const
   return 0;
 }
 
+int Cassie2dBatchBaselineMoments(CassieBatch* h, int task, const void* obs_dev, const void* returns_dev, const uint8_t* done_dev,
+                                 const int32_t* path_start_dev, int n_policy_steps, int32_t* path_index_dev,
+                                 double* moments_dev, void* stream) {
+  if (!h || !obs_dev || !returns_dev || !done_dev || !path_index_dev || !moments_dev) return fail("null argument");
+  if (task != 0 && task != 1) return fail("bad task");
+  if (set_device(h)) return -1;
+  BaselineArgs a{};
+  a.obs = obs_dev; a.ret = returns_dev; a.done = done_dev; a.start = path_start_dev; a.idx = path_index_dev; a.moments = moments_dev;
+  a.odim = task == 1 ? 26 : 17; a.T_steps = n_policy_steps; a.n = h->n;
+  DISPATCH(h, CU_OK(launch_baseline_moments<R>(a, (cudaStream_t)stream)));
+  return 0;
+}
+
+int Cassie2dBatchAdvantages(CassieBatch* h, int task, const void* obs_dev, const void* reward_dev, const uint8_t* done_dev,
+                            const int32_t* path_index_dev, const void* coeffs_dev, double gamma, double gae_lambda,
+                            int n_policy_steps, void* advantages_dev, void* values_dev, void* stream) {
+  if (!h || !obs_dev || !reward_dev || !done_dev || !path_index_dev || !coeffs_dev || !advantages_dev) return fail("null argument");
+  if (task != 0 && task != 1) return fail("bad task");
+  if (set_device(h)) return -1;
+  BaselineArgs a{};
+  a.obs = obs_dev; a.rew = reward_dev; a.done = done_dev; a.idx = const_cast<int32_t*>(path_index_dev); a.coeffs = coeffs_dev;
+  a.adv = advantages_dev; a.value = values_dev; a.odim = task == 1 ? 26 : 17; a.T_steps = n_policy_steps; a.n = h->n;
+  a.gamma = gamma; a.lambda = gae_lambda;
+  DISPATCH(h, CU_OK(launch_advantages<R>(a, (cudaStream_t)stream)));
+  return 0;
+}
+
 int Cassie2dBatchSquat(CassieBatch* h, int mode, int n_steps, const void* phase_dev, uint32_t* contact_mask_dev,
                        void* stream) {
   if (!h) return fail("null handle");

@@ -3,4 +3,6 @@
 namespace cassie {
 template cudaError_t launch_rollout<double>(const ModelPair<double>&, const BatchView<double>&, const RolloutArgs&, cudaStream_t);
 template cudaError_t launch_discounted_returns<double>(const void*, const uint8_t*, const void*, double, int, int, void*, cudaStream_t);
+template cudaError_t launch_baseline_moments<double>(const BaselineArgs&, cudaStream_t);
+template cudaError_t launch_advantages<double>(const BaselineArgs&, cudaStream_t);
 }

@@ -215,6 +215,129 @@ cudaError_t launch_discounted_returns(const void* rew, const uint8_t* done, cons
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------
+// LinearFeatureBaseline + advantages (rllab [EXT], used by trpo_cassie.py:29-41): features of a sample =
+// [clip(o, -10, 10), clip(o)^2, al, al^2, al^3, 1] with al = (step index within its path) / 100.
+// k_path_index recovers the in-path step index from the done flags; k_baseline_moments accumulates the
+// normal equations F'F (D x D) and F'y (D) over all T x n samples (the D x D solve itself is host-side
+// glue on 38 x 38 numbers); k_advantages evaluates the baseline and runs the backward GAE scan
+//   delta_t = r_t + gamma V_{t+1} - V_t,  A_t = delta_t + gamma lambda A_{t+1}   (V = 0 past a path end).
+constexpr int kMaxFeat = 2 * 26 + 4;
+
+template <typename T>
+__device__ __forceinline__ void baseline_features(const T* __restrict__ o, int odim, int step_in_path, T* f) {
+  for (int i = 0; i < odim; i++) {
+    T x = o[i];
+    x = x < T(-10) ? T(-10) : (x > T(10) ? T(10) : x);
+    f[i] = x;
+    f[odim + i] = x * x;
+  }
+  const T al = (T)step_in_path / T(100);
+  f[2 * odim] = al; f[2 * odim + 1] = al * al; f[2 * odim + 2] = al * al * al; f[2 * odim + 3] = T(1);
+}
+
+// in-path step index of every sample; start[n] (in/out, optional) carries the index across collect() calls
+template <typename T>
+__global__ void __launch_bounds__(128) k_path_index(const uint8_t* __restrict__ done, int T_steps, int n, const int32_t* start,
+                                                    int32_t* __restrict__ idx) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  int k = start ? start[e] : 0;
+  for (int t = 0; t < T_steps; t++) {
+    idx[(size_t)t * n + e] = k;
+    k = done[(size_t)t * n + e] ? 0 : k + 1;
+  }
+}
+
+// one CTA per chunk of samples: features staged in shared memory, thread p owns entries p, p + 256, ... of
+// the packed upper triangle (+ the F'y column); double accumulation, one atomicAdd per entry per CTA
+template <typename T>
+__global__ void __launch_bounds__(256) k_baseline_moments(const T* __restrict__ obs, const T* __restrict__ ret,
+                                                          const int32_t* __restrict__ idx, int odim, long n_samples,
+                                                          int chunk, double* __restrict__ out) {
+  const int D = 2 * odim + 4, n_ent = D * (D + 1) / 2 + D;
+  __shared__ T sf[32][kMaxFeat + 1];
+  double acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; q++) acc[q] = 0.0;
+  const long s0 = (long)blockIdx.x * chunk, s1 = s0 + chunk < n_samples ? s0 + chunk : n_samples;
+  for (long base = s0; base < s1; base += 32) {
+    const int cnt = (int)(s1 - base < 32 ? s1 - base : 32);
+    __syncthreads();
+    if (threadIdx.x < cnt) {
+      const long smp = base + threadIdx.x;
+      baseline_features(obs + smp * odim, odim, idx[smp], sf[threadIdx.x]);
+      sf[threadIdx.x][D] = ret[smp];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int p = threadIdx.x + 256 * q;
+      if (p < n_ent) {
+        int i, j;  // entry p -> (i, j): packed rows of the upper triangle, then the F'y column (j = D)
+        if (p < D * (D + 1) / 2) {
+          i = 0; int rem = p;
+          while (rem >= D - i) { rem -= D - i; i++; }
+          j = i + rem;
+        } else { i = p - D * (D + 1) / 2; j = D; }
+        double sacc = 0.0;
+        for (int c = 0; c < cnt; c++) sacc += (double)sf[c][i] * (double)sf[c][j];
+        acc[q] += sacc;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const int p = threadIdx.x + 256 * q;
+    if (p < n_ent) atomicAdd(out + p, acc[q]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_advantages(const T* __restrict__ obs, const T* __restrict__ rew,
+                                                    const uint8_t* __restrict__ done, const int32_t* __restrict__ idx,
+                                                    const T* __restrict__ coeffs, int odim, T gamma, T lambda, int T_steps, int n,
+                                                    T* __restrict__ adv, T* __restrict__ value) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int D = 2 * odim + 4;
+  T f[kMaxFeat];
+  T v_next = T(0), a_next = T(0);
+  for (int t = T_steps - 1; t >= 0; t--) {
+    const size_t i = (size_t)t * n + e;
+    baseline_features(obs + i * odim, odim, idx[i], f);
+    T v = T(0);
+    for (int c = 0; c < D; c++) v += f[c] * coeffs[c];
+    if (done[i]) { v_next = T(0); a_next = T(0); }   // np.append(baseline, 0): nothing beyond a path end
+    const T delta = rew[i] + gamma * v_next - v;
+    const T a = delta + gamma * lambda * a_next;
+    adv[i] = a;
+    if (value) value[i] = v;
+    v_next = v; a_next = a;
+  }
+}
+
+template <typename T>
+cudaError_t launch_baseline_moments(const BaselineArgs& a, cudaStream_t s) {
+  k_path_index<T><<<grid_for(a.n, 128), 128, 0, s>>>(a.done, a.T_steps, a.n, a.start, a.idx);
+  const long n_samples = (long)a.T_steps * a.n;
+  const int chunk = 4096;
+  const int D = 2 * a.odim + 4;
+  cudaError_t e = cudaMemsetAsync(a.moments, 0, sizeof(double) * (D * (D + 1) / 2 + D), s);
+  if (e != cudaSuccess) return e;
+  k_baseline_moments<T><<<(unsigned)((n_samples + chunk - 1) / chunk), 256, 0, s>>>((const T*)a.obs, (const T*)a.ret, a.idx, a.odim,
+                                                                                  n_samples, chunk, a.moments);
+  count_launch(); count_launch();
+  return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_advantages(const BaselineArgs& a, cudaStream_t s) {
+  k_advantages<T><<<grid_for(a.n, 128), 128, 0, s>>>((const T*)a.obs, (const T*)a.rew, a.done, a.idx, (const T*)a.coeffs, a.odim,
+                                                    (T)a.gamma, (T)a.lambda, a.T_steps, a.n, (T*)a.adv, (T*)a.value);
+  count_launch();
+  return cudaGetLastError();
+}
+
 template <typename T>
 cudaError_t launch_rollout(const ModelPair<T>& mp, const BatchView<T>& v, const RolloutArgs& a, cudaStream_t s) {
   RolloutDev<T> d;

@@ -21,7 +21,7 @@ BATCH_SYMBOLS = ["CassieGetLastError", "Cassie2dBatchInit", "Cassie2dBatchDestro
                  "Cassie2dBatchPrecision", "Cassie2dBatchDevice", "Cassie2dBatchRealSize", "Cassie2dBatchReset",
                  "Cassie2dBatchSetState", "Cassie2dBatchGetGeneralState", "Cassie2dBatchGetOperationalSpaceState",
                  "Cassie2dBatchStep", "Cassie2dBatchEnvStep", "Cassie2dBatchEnvReset", "Cassie2dBatchSetTrajectory",
-                 "Cassie2dBatchSquat", "Cassie2dBatchRollout", "Cassie2dBatchDiscountedReturns", "Cassie2dBatchStepHost", "Cassie2dBatchEnvStepHost", "Cassie2dBatchSquatHost",
+                 "Cassie2dBatchSquat", "Cassie2dBatchRollout", "Cassie2dBatchDiscountedReturns", "Cassie2dBatchBaselineMoments", "Cassie2dBatchAdvantages", "Cassie2dBatchStepHost", "Cassie2dBatchEnvStepHost", "Cassie2dBatchSquatHost",
                  "Cassie2dBatchGetStats", "Cassie2dBatchSetWarmStart", "Cassie2dBatchGetWarmStart", "Cassie2dBatchSync", "CassieMeasureFp32Peak", "CassieKernelLaunchCount"]
 
 _lib = None
@@ -54,6 +54,8 @@ def load():
     L.Cassie2dBatchSetTrajectory.argtypes = [vp, ct.POINTER(cd), ci, cd]
     L.Cassie2dBatchSquat.argtypes = [vp, ci, ci, vp, vp, vp]
     L.Cassie2dBatchDiscountedReturns.argtypes = [vp, vp, vp, vp, cd, ci, vp, vp]
+    L.Cassie2dBatchBaselineMoments.argtypes = [vp, ci, vp, vp, vp, vp, ci, vp, vp, vp]
+    L.Cassie2dBatchAdvantages.argtypes = [vp, ci, vp, vp, vp, vp, vp, cd, cd, ci, vp, vp, vp]
     L.Cassie2dBatchRollout.argtypes = [vp, ci, ci, vp, ci, ci, ci, ci, ci, ci, ct.c_ulonglong, ct.c_uint, vp, vp, vp, vp, vp, vp]
     L.Cassie2dBatchStepHost.argtypes = [vp, ci, vp, ci, vp]
     L.Cassie2dBatchEnvStepHost.argtypes = [vp, ci, ci, vp, ci, ci, vp, vp, vp]

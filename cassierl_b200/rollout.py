@@ -110,6 +110,42 @@ class RolloutCollector:
                                                           int(self._T), ret.data_ptr(), _stream_ptr()), "DiscountedReturns")
         return ret
 
+    def fit_baseline(self, returns, reg_coeff=1e-5):
+        """LinearFeatureBaseline.fit (rllab [EXT]): normal equations accumulated on device, the
+        D x D solve (D = 2 obs_dim + 4) on the host.  Returns the coefficient tensor (device)."""
+        b = self.batch
+        D = 2 * self.obs_dim + 4
+        T = self._T
+        if getattr(self, "_pidx", None) is None or self._pidx.shape[0] != T:
+            self._pidx = torch.empty((T, b.n), dtype=torch.int32, device=b.device)
+        mom = torch.empty(D * (D + 1) // 2 + D, dtype=torch.float64, device=b.device)
+        with torch.cuda.device(b.device):
+            _lib.check(b.L.Cassie2dBatchBaselineMoments(b.h, self.task, self.obs.data_ptr(), returns.data_ptr(), self.done.data_ptr(),
+                                                        None, int(T), self._pidx.data_ptr(), mom.data_ptr(), _stream_ptr()), "BaselineMoments")
+        m = mom.cpu().numpy()
+        FtF = np.zeros((D, D)); iu = np.triu_indices(D)
+        FtF[iu] = m[:D * (D + 1) // 2]; FtF = FtF + FtF.T - np.diag(np.diag(FtF))
+        Fty = m[D * (D + 1) // 2:]
+        coeffs = None
+        for _ in range(5):                           # rllab retries with a 10x larger regulariser on NaNs
+            coeffs = np.linalg.lstsq(FtF + reg_coeff * np.eye(D), Fty, rcond=None)[0]
+            if not np.any(np.isnan(coeffs)):
+                break
+            reg_coeff *= 10
+        self.baseline_coeffs = torch.tensor(coeffs, dtype=b.dtype, device=b.device)
+        return self.baseline_coeffs
+
+    def advantages(self, gamma=0.99, gae_lambda=1.0, coeffs=None):
+        """GAE advantages and baseline values [T, N] of the last collect() (after fit_baseline)."""
+        b = self.batch
+        c = self.baseline_coeffs if coeffs is None else coeffs
+        adv = torch.empty_like(self.rew); val = torch.empty_like(self.rew)
+        with torch.cuda.device(b.device):
+            _lib.check(b.L.Cassie2dBatchAdvantages(b.h, self.task, self.obs.data_ptr(), self.rew.data_ptr(), self.done.data_ptr(),
+                                                   self._pidx.data_ptr(), c.data_ptr(), float(gamma), float(gae_lambda), int(self._T),
+                                                   adv.data_ptr(), val.data_ptr(), _stream_ptr()), "Advantages")
+        return adv, val
+
     def paths(self, policy, envs=None):
         """Split the last collect() into rllab path dicts (one per finished or truncated episode)."""
         obs, act, mean, rew, done = (x.cpu().numpy() for x in (self.obs, self.act, self.mean, self.rew, self.done))

@@ -147,6 +147,21 @@ int Cassie2dBatchRollout(CassieBatch* h, int task, int mode, const void* params_
 int Cassie2dBatchDiscountedReturns(CassieBatch* h, const void* reward_dev, const uint8_t* done_dev, const void* tail_dev,
                                    double gamma, int n_policy_steps, void* returns_dev, void* stream);
 
+/* LinearFeatureBaseline and GAE advantages over the [T][n] rollout buffers (rllab [EXT]; trpo_cassie.py:29-41
+ * constructs LinearFeatureBaseline, TRPO(discount=0.99)).  Features of a sample: [clip(o,-10,10), clip(o)^2,
+ * al, al^2, al^3, 1], al = in-path step index / 100, D = 2 odim + 4.
+ * BaselineMoments: path_index_dev int32 [T][n] (out) = in-path step index (path_start_dev int32 [n], optional,
+ *   = index at which each env enters this buffer); moments_dev double [D(D+1)/2 + D] (out) = packed upper
+ *   triangle of F'F row by row, then F'returns.  Solve (F'F + reg I) w = F'y on the host (38 x 38).
+ * Advantages: delta_t = r_t + gamma V_{t+1} - V_t, A_t = delta_t + gamma lambda A_{t+1}, V = features . coeffs,
+ *   restarted at every done != 0; values_dev (optional) receives V. */
+int Cassie2dBatchBaselineMoments(CassieBatch* h, int task, const void* obs_dev, const void* returns_dev, const uint8_t* done_dev,
+                                 const int32_t* path_start_dev, int n_policy_steps, int32_t* path_index_dev,
+                                 double* moments_dev, void* stream);
+int Cassie2dBatchAdvantages(CassieBatch* h, int task, const void* obs_dev, const void* reward_dev, const uint8_t* done_dev,
+                            const int32_t* path_index_dev, const void* coeffs_dev, double gamma, double gae_lambda,
+                            int n_policy_steps, void* advantages_dev, void* values_dev, void* stream);
+
 /* The squatting.py loop (squatting.py:8-16) on device: n_steps iterations of
  * standing_controller_jacobian (mode JACOBIAN, cassie2d.py:297-331) or
  * standing_controller_osc (mode OSC, cassie2d.py:263-295) with height target

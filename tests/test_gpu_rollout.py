@@ -124,3 +124,41 @@ def test_discounted_returns(R):
         dc = np.array([np.sum(r[i:] * 0.99 ** np.arange(len(r) - i)) for i in range(len(r))])
         e = p["env"]
     col.close()
+
+
+def test_linear_feature_baseline_and_gae(R):
+    """On-device LinearFeatureBaseline fit + GAE against a numpy restatement of rllab's
+    LinearFeatureBaseline / process_samples on the same paths (fp64 build)."""
+    n, T = 128, 40
+    col = R.RolloutCollector(n, task="stand", control_mode="Torque", precision=64, max_path_length=15, seed=11)
+    pol = R.GaussianMLPPolicy(col.obs_dim, col.act_dim, seed=4, dtype=torch.float64)
+    col.collect(pol, T)
+    ret = col.discounted_returns(0.99)
+    coeffs = col.fit_baseline(ret).cpu().numpy()
+    adv, val = col.advantages(0.99, 0.97)
+    adv, val = adv.cpu().numpy(), val.cpu().numpy()
+    paths = col.paths(pol)
+    feats, rets, spans = [], [], []
+    retn = ret.cpu().numpy(); done = col.done.cpu().numpy()
+    for p in paths:
+        o = np.clip(p["observations"], -10, 10); l = len(p["rewards"])
+        al = np.arange(l).reshape(-1, 1) / 100.0
+        feats.append(np.concatenate([o, o ** 2, al, al ** 2, al ** 3, np.ones((l, 1))], axis=1))
+    # paths() orders by env then time; rebuild the matching returns
+    k = 0
+    for e in range(n):
+        start = 0
+        ends = list(np.nonzero(done[:, e])[0]) + ([T - 1] if done[-1, e] == 0 else [])
+        for kk in ends:
+            rets.append(retn[start:kk + 1, e]); spans.append((e, start, kk + 1)); start = kk + 1
+    F = np.concatenate(feats); y = np.concatenate(rets)
+    want = np.linalg.lstsq(F.T @ F + 1e-5 * np.eye(F.shape[1]), F.T @ y, rcond=None)[0]
+    assert np.allclose(coeffs, want, rtol=1e-6, atol=1e-8)
+    for f, p, (e, a, b) in zip(feats, paths, spans):
+        v = f @ want
+        vb = np.append(v, 0.0) if (done[b - 1, e] != 0) else np.append(v, 0.0)
+        deltas = p["rewards"] + 0.99 * vb[1:] - vb[:-1]
+        want_adv = np.array([np.sum(deltas[i:] * (0.99 * 0.97) ** np.arange(len(deltas) - i)) for i in range(len(deltas))])
+        assert np.allclose(val[a:b, e], v, rtol=1e-8, atol=1e-8)
+        assert np.allclose(adv[a:b, e], want_adv, rtol=1e-7, atol=1e-7)
+    col.close()
