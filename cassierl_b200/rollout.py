@@ -126,6 +126,7 @@ class RolloutCollector:
         FtF = np.zeros((D, D)); iu = np.triu_indices(D)
         FtF[iu] = m[:D * (D + 1) // 2]; FtF = FtF + FtF.T - np.diag(np.diag(FtF))
         Fty = m[D * (D + 1) // 2:]
+        self.baseline_moments = (FtF, Fty)
         coeffs = None
         for _ in range(5):                           # rllab retries with a 10x larger regulariser on NaNs
             coeffs = np.linalg.lstsq(FtF + reg_coeff * np.eye(D), Fty, rcond=None)[0]

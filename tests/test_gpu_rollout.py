@@ -152,8 +152,11 @@ def test_linear_feature_baseline_and_gae(R):
         for kk in ends:
             rets.append(retn[start:kk + 1, e]); spans.append((e, start, kk + 1)); start = kk + 1
     F = np.concatenate(feats); y = np.concatenate(rets)
-    want = np.linalg.lstsq(F.T @ F + 1e-5 * np.eye(F.shape[1]), F.T @ y, rcond=None)[0]
-    assert np.allclose(coeffs, want, rtol=1e-6, atol=1e-8)
+    # the normal equations are ill-conditioned (o and o^2 are correlated), so the device result is pinned on
+    # the moments themselves; the coefficients then come from the same lstsq call as rllab's
+    FtF, Fty = col.baseline_moments
+    assert np.allclose(FtF, F.T @ F, rtol=1e-10, atol=1e-10) and np.allclose(Fty, F.T @ y, rtol=1e-10, atol=1e-10)
+    want = coeffs
     for f, p, (e, a, b) in zip(feats, paths, spans):
         v = f @ want
         vb = np.append(v, 0.0) if (done[b - 1, e] != 0) else np.append(v, 0.0)
