@@ -31,12 +31,20 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(io.StringIO(out))); hdr, data = rows[1], rows[2:]
 ia, isamp = hdr.index("Instructions Executed"), hdr.index("# Samples")
 ex = np.array([int(r[ia]) if r[ia].isdigit() else 0 for r in data]); sm = np.array([int(r[isamp]) if r[isamp].isdigit() else 0 for r in data])
+def col(name):
+    i = hdr.index(name)
+    return np.array([int(r[i]) if r[i].isdigit() else 0 for r in data])
+st_long, st_noi, st_wait = col("stall_long_sb"), col("stall_no_inst"), col("stall_wait")
 n = min(len(lines), len(data))
 print("SASS lines: cubin %d, report %d%s" % (len(lines), len(data), "" if len(lines) == len(data) else "  (MISMATCH: stale library?)"))
 size = collections.Counter(); s_ = collections.Counter(); e_ = collections.Counter()
+l_ = collections.Counter(); n_ = collections.Counter(); w_ = collections.Counter()
 for i in range(n):
     f, l = lines[i]; k = (f, l // bucket * bucket); size[k] += 1; s_[k] += sm[i]; e_[k] += ex[i]
-print("%-32s %8s %9s %8s" % ("source region", "SASS", "samples%", "exec%"))
-for k, v in s_.most_common(30):
-    print("%-24s %6d %8d %8.1f%% %7.1f%%" % (k[0], k[1], size[k], 100 * v / sm.sum(), 100 * e_[k] / ex.sum()))
+    l_[k] += st_long[i]; n_[k] += st_noi[i]; w_[k] += st_wait[i]
+# the last three columns are shares of ALL samples of the kernel spent in that stall reason inside the region
+print("%-32s %8s %9s %8s %8s %8s %8s" % ("source region", "SASS", "samples%", "exec%", "long_sb%", "no_inst%", "wait%"))
+for k, v in s_.most_common(int(os.environ.get("TOP", "30"))):
+    print("%-24s %6d %8d %8.1f%% %7.1f%% %7.1f%% %7.1f%% %7.1f%%" % (k[0], k[1], size[k], 100 * v / sm.sum(), 100 * e_[k] / ex.sum(),
+          100 * l_[k] / sm.sum(), 100 * n_[k] / sm.sum(), 100 * w_[k] / sm.sum()))
 print("never executed SASS: %d of %d" % (int((ex[:n] == 0).sum()), n))
