@@ -197,13 +197,18 @@ CASSIE_HD void osc_control(const PlanarModel<T>& m, const Kin<T>& k, const T* qd
       for (int c = 0; c < 4; c++) x[i] -= d.T1[i][c] * y[c];
     }
     solve(d.LD, d.Dinv, x);  // x = Z_r
-    CASSIE_UNROLL
-    for (int a = 0; a < kNU; a++) {
-      T v = T(0);
+    {  // u columns: gear * Z_r[actuated dof]; dof-major so that every x[i] is touched once (x lives in spill slots)
+      T v[kNU];
       CASSIE_UNROLL
-      for (int i = 3; i < kNV; i++)
-        if (m.act_dof[a] == i) v = x[i];
-      E[r][a] = (double)(m.act_gear[a] * v);
+      for (int a = 0; a < kNU; a++) v[a] = T(0);
+      CASSIE_UNROLL
+      for (int i = 3; i < kNV; i++) {
+        const T xi = x[i];
+        CASSIE_UNROLL
+        for (int a = 0; a < kNU; a++) v[a] = m.act_dof[a] == i ? xi : v[a];
+      }
+      CASSIE_UNROLL
+      for (int a = 0; a < kNU; a++) E[r][a] = (double)(m.act_gear[a] * v[a]);
     }
     CASSIE_UNROLL
     for (int s = 0; s < 4; s++) {
