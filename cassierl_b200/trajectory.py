@@ -6,6 +6,7 @@ Restates rllab/envs/cassie2d_trajectory.py (CassieRL/cassierl): `stepdata.bin` w
 yaw, spring and rod-hinge columns) and the time -> row lookup (:16-19), vectorised.
 """
 import os
+import random
 
 import numpy as np
 
@@ -25,8 +26,47 @@ def _euler_y(w, x, y, z):
     return np.arcsin(np.clip(2.0 * (w * y - z * x), -1.0, 1.0))
 
 
+def quat2eul(w, x, y, z):
+    """ZYX Euler angles (Z, Y, X) of a quaternion, the reference's Cassie2dTraj.quat2eul (:136-151)."""
+    X = np.arctan2(2.0 * (w * x + y * z), 1.0 - 2.0 * (x * x + y * y))
+    Y = _euler_y(w, x, y, z)
+    Z = np.arctan2(2.0 * (w * z + x * y), 1.0 - 2.0 * (y * y + z * z))
+    return Z, Y, X
+
+
+class Cassie3dTraj:
+    """The raw 3-D table of `stepdata.bin` (reference class of the same name, :5-28): .time .qpos(35) .qvel(32)
+    .torque(10) .mpos(10) .mvel(10), state(t), action(t), sample()."""
+
+    def __init__(self, filepath):
+        data = np.fromfile(filepath, dtype=np.float64).reshape((-1, ROW))
+        self.time = data[:, 0].copy()
+        self.qpos = data[:, 1:36].copy()
+        self.qvel = data[:, 36:68].copy()
+        self.torque = data[:, 68:78].copy()
+        self.mpos = data[:, 78:88].copy()
+        self.mvel = data[:, 88:98].copy()
+
+    def index(self, t):
+        tmax = self.time[-1]
+        return int((t % tmax) / tmax * len(self.time))
+
+    def state(self, t):
+        i = self.index(t)
+        return (self.qpos[i], self.qvel[i])
+
+    def action(self, t):
+        i = self.index(t)
+        return (self.mpos[i], self.mvel[i], self.torque[i])
+
+    def sample(self):
+        """random-phase draw (:26-28): uses the `random` module like the reference, so `random.seed` reproduces it"""
+        i = random.randrange(len(self.time))
+        return (self.time[i], self.qpos[i], self.qvel[i])
+
+
 class Cassie2dTraj:
-    """Same interface as the reference class: .time .qpos .qvel .torque, state(t), action(t)."""
+    """Same interface as the reference class: .time .qpos .qvel .torque, state(t), action(t), sample()."""
 
     def __init__(self, filepath=None):
         if filepath is None or filepath.endswith(".npz"):
@@ -56,6 +96,13 @@ class Cassie2dTraj:
     def action(self, t):
         i = self.index(t)
         return (self.mpos[i], self.mvel[i], self.torque[i])
+
+    def sample(self):
+        i = random.randrange(len(self.time))
+        return (self.time[i], self.qpos[i], self.qvel[i])
+
+    def quat2eul(self, w, x, y, z):
+        return quat2eul(w, x, y, z)
 
     def save_npz(self, path):
         np.savez_compressed(path, time=self.time, qpos=self.qpos, qvel=self.qvel, torque=self.torque,
