@@ -257,6 +257,12 @@ def run_native(args):
     stats = torch.stack([s[:, 1].double().sum(), (s[:, 1] < 0.5).double().sum(), (~torch.isfinite(s).all(dim=1)).double().sum()])
     if world > 1:
         dist.all_reduce(stats)
+    # constraint rows / PGS sweeps / QP iterations of the LAST sim step (rank 0's shard): which solver tier the
+    # workload sits in at the end of the timed window (<= 8 rows narrow, <= 12 wide register path, more = cold path)
+    st = b.stats().double()
+    solver_stats = {"rows_mean": float(st[:, 0].mean().item()), "rows_max": int(st[:, 0].max().item()),
+                    "pgs_sweeps_mean": float(st[:, 1].mean().item()), "qp_iters_mean": float(st[:, 2].mean().item()),
+                    "qp_not_optimal": int((st[:, 3] != 0).sum().item())}
     value = world * n * sub * args.steps / (ms_max * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI entry points (pinned host memory in and out)
@@ -328,7 +334,7 @@ def run_native(args):
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks,
             "stats": {"mean_pelvis_z": float(stats[0].item()) / (n * world), "envs_below_0.5m": int(stats[1].item()),
-                      "non_finite_envs": int(stats[2].item())},
+                      "non_finite_envs": int(stats[2].item()), "last_step": solver_stats},
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(wl, args.cpu_seconds)

