@@ -61,6 +61,9 @@ template <> struct Num<float> {
   static CASSIE_HD float abs_(float a) { return fabsf(a); }
   static CASSIE_HD float pow_(float a, float b) { return powf(a, b); }
   static CASSIE_HD float exp_(float a) { return expf(a); }
+  static CASSIE_HD float max_(float a, float b) { return fmaxf(a, b); }   // one FMNMX, no predicate round trip
+  static CASSIE_HD float min_(float a, float b) { return fminf(a, b); }
+  static constexpr bool kExactConeTest = false;
 };
 template <> struct Num<double> {
   static CASSIE_HD void sincos_(double a, double* s, double* c) { sincos_reduced(a, s, c); }
@@ -68,6 +71,9 @@ template <> struct Num<double> {
   static CASSIE_HD double abs_(double a) { return fabs(a); }
   static CASSIE_HD double pow_(double a, double b) { return pow(a, b); }
   static CASSIE_HD double exp_(double a) { return exp(a); }
+  static CASSIE_HD double max_(double a, double b) { return fmax(a, b); }
+  static CASSIE_HD double min_(double a, double b) { return fmin(a, b); }
+  static constexpr bool kExactConeTest = true;
 };
 
 // j is an ancestor-or-self of dof i in the kinematic tree (j <= i)
@@ -837,25 +843,25 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
   CASSIE_UNROLL
   for (int i = 0; i < NR; i++) inv[i] = T(1) / A[tri(i, i)];
   const T scale = T(1) / (m.meaninertia * T(kNV));
-  const T inv_mu = T(1) / m.con_mu;
+  const T mu = m.con_mu, inv_mu = T(1) / mu;
   int iter = 0;
-  // Latency-oriented sweep: everything that only depends on the forces of the PREVIOUS sweep (the
-  // upper-triangle part of each residual `hi`, the ray-update denominators `rden`) is kept off the
-  // Gauss-Seidel chain, which is then one FMA + one add per row plus the projection.  The per-block
-  // "cost went up -> revert" test of mj_solPGS is dropped here: every block update is an exact
-  // minimisation of a convex sub-problem, so the change is <= 0 in exact arithmetic and the test can only
-  // fire on rounding noise (the general path keeps it).
-  // Software-pipelined: the previous-sweep part of every residual for sweep k+1 (hn) is accumulated DURING
-  // sweep k, right after each force is final (ascending c, i.e. the summation order of a plain row sum), which
-  // puts those 78 FMAs into the slack of the dependency chain instead of in front of it (+9 % on the PD env step).
-  T hi[NR], rden[NC > 0 ? NC : 1];
+  // Latency-oriented sweep.  One accumulator per row carries its residual: acc_i = b_i + sum_c A_ic f_c with the
+  // forces of the previous sweep for c >= i and of this sweep for c < i.  Whenever a force is final it is
+  // "published": every other row adds its term (independent FMAs, they fill the issue slots under the
+  // Gauss-Seidel dependency chain), and the row itself restarts its accumulator for the next sweep
+  // (acc_i = b_i + A_ii f_i, to which the later columns then add in ascending order -- no incremental drift:
+  // every residual is a fresh sum of <= NR terms).  The chain through the freshly updated forces is one FMA
+  // per row plus the projection.  The per-block "cost went up -> revert" test of mj_solPGS is dropped here:
+  // every block update is an exact minimisation of a convex sub-problem, so the change is <= 0 in exact
+  // arithmetic and the test can only fire on rounding noise (the general path keeps it).
+  T acc[NR], rden[NC > 0 ? NC : 1];
   CASSIE_UNROLL
   for (int i = 0; i < NR; i++) {
     T sacc = b[i];
     CASSIE_UNROLL
     for (int c = 0; c < NR; c++)
       if (c >= i) sacc += A[tri(i, c)] * f[c];
-    hi[i] = sacc;
+    acc[i] = sacc;
   }
   CASSIE_UNROLL
   for (int p = 0; p < NC; p++) {
@@ -865,63 +871,54 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
     rden[p] = denom >= T(kMinVal) ? T(1) / denom : T(0);
   }
   while (iter < m.iterations) {
-    T hn[NR];
-    CASSIE_UNROLL
-    for (int i = 0; i < NR; i++) hn[i] = b[i];
     T improvement = T(0);
     CASSIE_UNROLL
-    for (int i = 0; i < NS; i++) {
-      T lo = T(0);
-      CASSIE_UNROLL
-      for (int c = 0; c < NR; c++)
-        if (c < i) lo += A[tri(i, c)] * f[c];
-      const T res = hi[i] + lo;
+    for (int i = 0; i < NS; i++) {  // scalar rows: connects unbounded, joint limits f >= 0
+      const T res = acc[i];
       T fn = f[i] - res * inv[i];
-      if (i >= 4) fn = fn < T(0) ? T(0) : fn;
+      if (i >= 4) fn = Num<T>::max_(fn, T(0));
       const T d = fn - f[i];
       f[i] = fn;
-      improvement -= T(0.5) * d * d * A[tri(i, i)] + d * res;
+      improvement -= d * (T(0.5) * d * A[tri(i, i)] + res);
       CASSIE_UNROLL
-      for (int rr = 0; rr < NR; rr++)
-        if (rr <= i) hn[rr] += A[tri(rr, i)] * fn;
+      for (int rr = 0; rr < NR; rr++) acc[rr] = rr == i ? b[i] + A[tri(i, i)] * fn : acc[rr] + A[tri(rr, i)] * fn;
     }
     CASSIE_UNROLL
-    for (int p = 0; p < NC; p++) {
+    for (int p = 0; p < NC; p++) {  // elliptic contact: normal + one tangent, updated as a pair
       const int i = NS + 2 * p;
-      T lo0 = T(0), lo1 = T(0);
-      CASSIE_UNROLL
-      for (int c = 0; c < NR; c++)
-        if (c < i) { lo0 += A[tri(i, c)] * f[c]; lo1 += A[tri(i + 1, c)] * f[c]; }
       const T old0 = f[i], old1 = f[i + 1];
       const T A00 = A[tri(i, i)], A01 = A[tri(i + 1, i)], A11 = A[tri(i + 1, i + 1)];
-      const T res0 = hi[i] + lo0;
-      const T res1 = hi[i + 1] + A01 * old0 + lo1;
-      T fa = old0 - res0 * inv[i];
-      fa = fa < T(0) ? T(0) : fa;
-      T x = -(old0 * res0 + old1 * res1) * rden[p];
-      x = x < T(-1) ? T(-1) : x;
+      const T res0 = acc[i];
+      const T res1 = acc[i + 1] + A01 * old0;  // row i+1 has not seen column i of this pair yet: old force
+      // (a) normal / ray update
+      const T fa = Num<T>::max_(old0 - res0 * inv[i], T(0));
+      const T x = Num<T>::max_(-(old0 * res0 + old1 * res1) * rden[p], T(-1));
       const T f0 = old0 < T(kMinVal) ? fa : old0 + x * old0;
+      // (b) friction update with the normal force fixed (mju_QCQP2 collapses to a clamp)
       const T bc = (res1 - A11 * old1 - A01 * old0) + A01 * f0;
       T v = -bc * inv[i + 1];
-      const T vs = v * inv_mu;
-      const T lim = m.con_mu * f0;
-      v = (vs * vs - f0 * f0 >= T(1e-10)) ? (v > T(0) ? lim : -lim) : v;
+      const T lim = mu * f0;
+      if (Num<T>::kExactConeTest) {
+        const T vs = v * inv_mu;
+        v = (vs * vs - f0 * f0 >= T(1e-10)) ? (v > T(0) ? lim : -lim) : v;
+      } else {
+        // fp32: plain clamp (two FMNMX instead of a compare -> predicate -> select chain).  It differs from the
+        // test above only inside its 1e-10 guard band, |v| in [lim, mu sqrt(f0^2 + 1e-10)): below 1e-5 N.
+        v = Num<T>::min_(Num<T>::max_(v, -lim), lim);
+      }
       const T f1 = f0 < T(kMinVal) ? T(0) : v;
       const T d0 = f0 - old0, d1 = f1 - old1;
-      improvement -= T(0.5) * (d0 * (A00 * d0 + A01 * d1) + d1 * (A01 * d0 + A11 * d1)) + d0 * res0 + d1 * res1;
+      improvement -= d0 * (T(0.5) * d0 * A00 + A01 * d1 + res0) + d1 * (T(0.5) * d1 * A11 + res1);
       f[i] = f0;
       f[i + 1] = f1;
       CASSIE_UNROLL
       for (int rr = 0; rr < NR; rr++)
-        if (rr <= i) hn[rr] += A[tri(rr, i)] * f0;
+        if (rr != i + 1) acc[rr] = rr == i ? b[i] + A00 * f0 : acc[rr] + A[tri(rr, i)] * f0;
       CASSIE_UNROLL
-      for (int rr = 0; rr < NR; rr++)
-        if (rr <= i + 1) hn[rr] += A[tri(rr, i + 1)] * f1;
+      for (int rr = 0; rr < NR; rr++) acc[rr] = rr == i + 1 ? b[i + 1] + A11 * f1 : acc[rr] + A[tri(rr, i + 1)] * f1;
       const T denom = f0 * (A00 * f0 + A01 * f1) + f1 * (A01 * f0 + A11 * f1);
       rden[p] = denom >= T(kMinVal) ? T(1) / denom : T(0);
     }
-    CASSIE_UNROLL
-    for (int i = 0; i < NR; i++) hi[i] = hn[i];
     iter++;
     if (improvement * scale < m.tolerance) break;
   }

@@ -43,6 +43,9 @@ template <> struct Num<CountD> {
   static CountD abs_(CountD a) { return CountD(fabs(a.v)); }
   static CountD pow_(CountD a, CountD b) { g_ops.trig++; return CountD(pow(a.v, b.v)); }
   static CountD exp_(CountD a) { g_ops.trig++; return CountD(exp(a.v)); }
+  static CountD max_(CountD a, CountD b) { return CountD(fmax(a.v, b.v)); }
+  static CountD min_(CountD a, CountD b) { return CountD(fmin(a.v, b.v)); }
+  static constexpr bool kExactConeTest = true;
 };
 }  // namespace cassie
 
