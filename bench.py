@@ -131,13 +131,52 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region: NVML polled every 5 ms from a thread (a launch list of
+    30 x 1.8 ms is over before `nvidia-smi -lms 100` prints its first line); nvidia-smi is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    MASKS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, uuid=None):
+        self.index, self.uuid, self.rows, self.proc = index, uuid, [], None
+        self.nvml, self.handle, self.thread, self.stop_flag = None, None, None, threading.Event()
+        self.sm, self.mask, self.sm_max = [], 0, None
+
+    def _nvml_open(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        if self.uuid:
+            for u in (self.uuid, self.uuid.encode()):
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(u)
+                    break
+                except Exception:
+                    h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.nvml, self.handle = pynvml, h
+        self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+    def _poll(self):
+        n, h = self.nvml, self.handle
+        reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+                self.mask |= int(reasons(h))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            self._nvml_open()
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -152,6 +191,12 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag.set()
+            self.thread.join(timeout=1)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+                    "reasons": sorted(name for name, bit in self.MASKS if self.mask & bit), "samples": len(self.sm),
+                    "source": "nvml, 5 ms poll"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -168,7 +213,7 @@ class ClockSampler:
                     if val.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ----------------------------------------------------------------------------- native arm
@@ -233,7 +278,11 @@ def run_native(args):
     for k in range(args.warmup):
         one_step(k)
     barrier()
-    sampler = ClockSampler(local)
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local, uuid)
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
