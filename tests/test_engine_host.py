@@ -264,4 +264,6 @@ def test_osc_random_actions_match_oracle(harness, oracle, omodel):
                 assert o["qp"][0, 1] == 0
                 iters.append(o["qp"][0, 0])
     assert worst < 1e-6, worst
-    assert np.mean(iters) < 40, np.mean(iters)
+    # every call of this loop starts from the EMPTY partition (the harness does not carry qp_set across calls):
+    # greedy single exchanges need 6.7 iterations on average, 17 at worst here (was ~30 / >100 with Murty's rule only)
+    assert np.mean(iters) < 10 and np.max(iters) <= 40, (np.mean(iters), np.max(iters))
