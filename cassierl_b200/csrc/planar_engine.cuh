@@ -1029,7 +1029,15 @@ CASSIE_HD void physics_step(const PlanarModel<T>& m, const PlanarModel<TG>& mg, 
 #else
   const bool fast_ok = true;
 #endif
-  if (fast_ok && !rare_rows_active(m, cp, q)) {
+  // The tier is chosen per WARP: lanes of one warp that took different tiers would run them one after the other,
+  // and the middle tier of constraints_cold solves the common regime as well (its limit slots stay empty).
+  const bool rare = !fast_ok || rare_rows_active(m, cp, q);
+#ifdef __CUDA_ARCH__
+  const bool warp_rare = __any_sync(__activemask(), rare);
+#else
+  const bool warp_rare = rare;
+#endif
+  if (!warp_rare) {
     // common regime: 4 connect rows + <= 4 toe contacts, everything in registers
     mask = make_rows<false>(m, k, cp, q, qd, r, (int*)nullptr);
     // 8-row (two contacts) or 12-row variant, chosen per WARP so that lanes never run both
