@@ -13,6 +13,11 @@ namespace cassie {
 #define CASSIE_BLOCK 64
 #endif
 constexpr int kBlock = CASSIE_BLOCK;
+// resident CTAs per SM the register allocation is sized for: 1 = all 255 registers (one warp per scheduler at
+// 16384 envs anyway); larger values trade spills for occupancy on very large batches (profiles/r1_variants.txt)
+#ifndef CASSIE_MIN_BLOCKS
+#define CASSIE_MIN_BLOCKS 1
+#endif
 // With several warps per CTA, a barrier per simulator step keeps them in lock step so that they share
 // instruction-cache fills (instruction fetch is the top stall of the step kernels).
 __device__ __forceinline__ void step_barrier() {
@@ -26,7 +31,7 @@ template <int MODE, typename T>
 __device__ __forceinline__ const auto& ctrl_model(const ModelPair<T>& mp) {
   if constexpr (MODE == kModeOsc) return mp.ctrl_d;
   else return mp.ctrl;
-}  // one warp per CTA: 16384 envs -> 512 CTAs spread over 148 SMs x 4 SMSPs
+}
 
 template <typename T>
 __device__ __forceinline__ void load_env(const BatchView<T>& v, int e, T q[kNV], T qd[kNV], T w[kNV]) {
@@ -85,7 +90,7 @@ __device__ __forceinline__ void state26_to_q(const T* s, T q[kNV], T qd[kNV]) {
 // ---------------------------------------------------------------------------------------
 // n_substeps x Step* (Cassie2d.cpp:86-209) with a held action
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v,
+__global__ void __launch_bounds__(kBlock, CASSIE_MIN_BLOCKS) k_step(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v,
                                                   const T* __restrict__ action, int n_sub, uint32_t* mask) {
   const int e = blockIdx.x * kBlock + threadIdx.x;
   if (e >= v.n) return;
@@ -149,7 +154,7 @@ __device__ __forceinline__ void write_obs(const BatchView<T>& v, int task, int e
 }
 
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kBlock) k_env_step(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v,
+__global__ void __launch_bounds__(kBlock, CASSIE_MIN_BLOCKS) k_env_step(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v,
                                                       const __grid_constant__ EnvStepDev<T> a) {
   const int e_raw = blockIdx.x * kBlock + threadIdx.x;
   const bool active = e_raw < v.n;   // inactive lanes shadow the last env (they must reach the barriers)
@@ -238,7 +243,7 @@ __global__ void __launch_bounds__(128) k_env_reset(const __grid_constant__ Model
 // ---------------------------------------------------------------------------------------
 // squatting.py:8-16 with standing_controller_jacobian / standing_controller_osc in the loop
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kBlock) k_squat(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v,
+__global__ void __launch_bounds__(kBlock, CASSIE_MIN_BLOCKS) k_squat(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v,
                                                    const T* __restrict__ phase, int n_steps, uint32_t* mask) {
   const int e_raw = blockIdx.x * kBlock + threadIdx.x;
   const bool active = e_raw < v.n;   // inactive lanes shadow the last env (they must reach the barriers)

@@ -63,7 +63,7 @@ struct RolloutDev {
 };
 
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kBlock) k_rollout(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v,
+__global__ void __launch_bounds__(kBlock, CASSIE_MIN_BLOCKS) k_rollout(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v,
                                                      const __grid_constant__ RolloutDev<T> a) {
   constexpr int adim = action_dim(MODE);
   const int odim = a.task == kTaskStand ? 17 : 26;
