@@ -63,6 +63,17 @@ template <> struct Num<float> {
   static CASSIE_HD float exp_(float a) { return expf(a); }
   static CASSIE_HD float max_(float a, float b) { return fmaxf(a, b); }   // one FMNMX, no predicate round trip
   static CASSIE_HD float min_(float a, float b) { return fminf(a, b); }
+  // reciprocal of a value known to be in the normal range: one MUFU.RCP (a plain 1.0f / a carries ~8 instructions of
+  // range scaling around it even with -prec-div=false)
+  static CASSIE_HD float rcp_(float a) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+#else
+    return 1.0f / a;
+#endif
+  }
   static constexpr bool kExactConeTest = false;
 };
 template <> struct Num<double> {
@@ -73,6 +84,7 @@ template <> struct Num<double> {
   static CASSIE_HD double exp_(double a) { return exp(a); }
   static CASSIE_HD double max_(double a, double b) { return fmax(a, b); }
   static CASSIE_HD double min_(double a, double b) { return fmin(a, b); }
+  static CASSIE_HD double rcp_(double a) { return 1.0 / a; }
   static constexpr bool kExactConeTest = true;
 };
 
@@ -317,7 +329,7 @@ template <typename T>
 CASSIE_HD void factor(T M[kNV][kNV], T Dinv[kNV]) {
   CASSIE_UNROLL
   for (int k = kNV - 1; k >= 0; k--) {
-    const T inv = T(1) / M[k][k];
+    const T inv = Num<T>::rcp_(M[k][k]);
     Dinv[k] = inv;
     CASSIE_UNROLL
     for (int i = kNV - 1; i >= 0; i--) {
@@ -812,7 +824,7 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
     CASSIE_UNROLL
     for (int i = NS; i < NR; i += 2) {
       const T N = jar[i] * mu, U1 = jar[i + 1] * m.con_mu, Tn = Num<T>::abs_(U1);
-      const T D0 = T(1) / r.R[i], D1 = T(1) / r.R[i + 1];
+      const T D0 = Num<T>::rcp_(r.R[i]), D1 = Num<T>::rcp_(r.R[i + 1]);
       T f0, f1;
       if (N >= mu * Tn || (Tn <= T(0) && N >= T(0))) { f0 = T(0); f1 = T(0); }
       else if (mu * N + Tn <= T(0) || (Tn <= T(0) && N < T(0))) { f0 = -D0 * jar[i]; f1 = -D1 * jar[i + 1]; }
@@ -841,7 +853,7 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
   }
   T inv[NR];
   CASSIE_UNROLL
-  for (int i = 0; i < NR; i++) inv[i] = T(1) / A[tri(i, i)];
+  for (int i = 0; i < NR; i++) inv[i] = Num<T>::rcp_(A[tri(i, i)]);
   const T scale = T(1) / (m.meaninertia * T(kNV));
   const T mu = m.con_mu, inv_mu = T(1) / mu;
   int iter = 0;
@@ -868,7 +880,7 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
     const int i = NS + 2 * p;
     const T o0 = f[i], o1 = f[i + 1];
     const T denom = o0 * (A[tri(i, i)] * o0 + A[tri(i + 1, i)] * o1) + o1 * (A[tri(i + 1, i)] * o0 + A[tri(i + 1, i + 1)] * o1);
-    rden[p] = denom >= T(kMinVal) ? T(1) / denom : T(0);
+    rden[p] = denom >= T(kMinVal) ? Num<T>::rcp_(denom) : T(0);
   }
   while (iter < m.iterations) {
     T improvement = T(0);
@@ -917,7 +929,7 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
       CASSIE_UNROLL
       for (int rr = 0; rr < NR; rr++) acc[rr] = rr == i + 1 ? b[i + 1] + A11 * f1 : acc[rr] + A[tri(rr, i + 1)] * f1;
       const T denom = f0 * (A00 * f0 + A01 * f1) + f1 * (A01 * f0 + A11 * f1);
-      rden[p] = denom >= T(kMinVal) ? T(1) / denom : T(0);
+      rden[p] = denom >= T(kMinVal) ? Num<T>::rcp_(denom) : T(0);
     }
     iter++;
     if (improvement * scale < m.tolerance) break;

@@ -45,6 +45,7 @@ template <> struct Num<CountD> {
   static CountD exp_(CountD a) { g_ops.trig++; return CountD(exp(a.v)); }
   static CountD max_(CountD a, CountD b) { return CountD(fmax(a.v, b.v)); }
   static CountD min_(CountD a, CountD b) { return CountD(fmin(a.v, b.v)); }
+  static CountD rcp_(CountD a) { return CountD(1.0) / a; }
   static constexpr bool kExactConeTest = true;
 };
 }  // namespace cassie
