@@ -388,12 +388,12 @@ CASSIE_COLD T impedance_pow(const T* si, T x) {
 template <typename T>
 CASSIE_HD T impedance(const T* si, T pos) {  // getimpedance [EXT], margin = 0
   if (si[0] == si[1] || si[2] <= T(kMinVal)) return T(0.5) * (si[0] + si[1]);
-  T x = Num<T>::abs_(pos / si[2]);
+  T x = Num<T>::abs_(pos * Num<T>::rcp_(si[2]));
   if (x >= T(1)) return si[1];
   if (x <= T(0)) return si[0];
   T y;
   if (si[4] == T(1)) y = x;
-  else if (si[4] == T(2)) y = x <= si[3] ? x * x / si[3] : T(1) - (T(1) - x) * (T(1) - x) / (T(1) - si[3]);
+  else if (si[4] == T(2)) y = x <= si[3] ? x * x * Num<T>::rcp_(si[3]) : T(1) - (T(1) - x) * (T(1) - x) * Num<T>::rcp_(T(1) - si[3]);
   else y = impedance_pow(si, x);
   return si[0] + y * (si[1] - si[0]);
 }
@@ -440,7 +440,7 @@ CASSIE_HD void push_row(Rows<T>& r, const T J8[8], int leg, int type, T diag, T 
   for (int c = 0; c < 8; c++) r.J[i][c] = J8[c];
   r.leg[i] = (signed char)leg;
   r.type[i] = (signed char)type;
-  const T Rv = (T(1) - imp) * diag / imp;
+  const T Rv = (T(1) - imp) * diag * Num<T>::rcp_(imp);   // imp in [1e-4, 1 - 1e-4]
   r.R[i] = Rv > T(kMinVal) ? Rv : T(kMinVal);
   const T vel = dot8_dense(J8, leg, qd);
   // aref, kept in b until qacc_smooth is known:  b = J qacc_smooth - aref
@@ -453,9 +453,9 @@ CASSIE_HD void kb_from_solref(const PlanarModel<T>& m, const T* solref, const T*
   if (tc > T(0) && tc < T(2) * m.timestep) tc = T(2) * m.timestep;  // refsafe
   const T dmax = solimp[1];
   T kd = dmax * dmax * tc * tc * solref[1] * solref[1];
-  K = T(1) / (kd > T(kMinVal) ? kd : T(kMinVal));
+  K = Num<T>::rcp_(kd > T(kMinVal) ? kd : T(kMinVal));
   T bd = dmax * tc;
-  Bd = T(2) / (bd > T(kMinVal) ? bd : T(kMinVal));
+  Bd = T(2) * Num<T>::rcp_(bd > T(kMinVal) ? bd : T(kMinVal));
 }
 
 // Position-level constraint violations: the loop-closure anchor mismatch and the signed distances of
@@ -816,7 +816,7 @@ CASSIE_HD int constraint_solve_fast(const PlanarModel<T>& m, Rows<T>& r, const T
   // warm start (mj_constraintUpdate [EXT] on jar = J qacc_warmstart - aref)
   CASSIE_UNROLL
   for (int i = 0; i < NS; i++) {
-    const T fw = -jar[i] / r.R[i];
+    const T fw = -jar[i] * Num<T>::rcp_(r.R[i]);          // R >= kMinVal
     f[i] = (i >= 4 && !(jar[i] < T(0))) ? T(0) : fw;   // limit rows: force only when violated
   }
   {
