@@ -1,7 +1,7 @@
 // CUDA kernels of the batched Cassie2d engine: one env per thread, env state in registers for
 // the whole launch (all substeps fused), constraint rows staged in thread-local memory and the
 // constraint system (A, b, f) in registers for the PGS sweeps, model constants in the kernel-parameter
-// constant bank (warp-uniform reads), 64-thread CTAs kept in lock step by one barrier per sim step.
+// constant bank (warp-uniform reads), 64-thread CTAs kept in lock step by one barrier per sim step (32 for OSC).
 // DESIGN.md sections 4-5 have the mapping rationale and the measured optimisation log.
 #pragma once
 #include "batch_state.h"
@@ -20,10 +20,12 @@ constexpr int kBlock = CASSIE_BLOCK;
 #endif
 // With several warps per CTA, a barrier per simulator step keeps them in lock step so that they share
 // instruction-cache fills (instruction fetch is the top stall of the step kernels).
+// The OSC kernels run one warp per CTA instead: they are bound by the L1 hit rate of the controller's thread-local
+// arrays, and 512 single-warp CTAs spread more evenly over the 148 SMs (3-4 warps each instead of 2-4): +2.5 %.
+constexpr int block_threads(int mode) { return mode == kModeOsc ? 32 : kBlock; }
+template <int B>
 __device__ __forceinline__ void step_barrier() {
-#if CASSIE_BLOCK > 32
-  __syncthreads();
-#endif
+  if constexpr (B > 32) __syncthreads();
 }
 
 // controller model of a mode: OSC runs in double in every build, the other modes in T
@@ -90,9 +92,9 @@ __device__ __forceinline__ void state26_to_q(const T* s, T q[kNV], T qd[kNV]) {
 // ---------------------------------------------------------------------------------------
 // n_substeps x Step* (Cassie2d.cpp:86-209) with a held action
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kBlock, CASSIE_MIN_BLOCKS) k_step(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v,
+__global__ void __launch_bounds__(block_threads(MODE), CASSIE_MIN_BLOCKS) k_step(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v,
                                                   const T* __restrict__ action, int n_sub, uint32_t* mask) {
-  const int e = blockIdx.x * kBlock + threadIdx.x;
+  const int e = blockIdx.x * block_threads(MODE) + threadIdx.x;
   if (e >= v.n) return;
   T q[kNV], qd[kNV], w[kNV], act[7], u[kNU];
   load_env(v, e, q, qd, w);
@@ -154,9 +156,9 @@ __device__ __forceinline__ void write_obs(const BatchView<T>& v, int task, int e
 }
 
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kBlock, CASSIE_MIN_BLOCKS) k_env_step(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v,
+__global__ void __launch_bounds__(block_threads(MODE), CASSIE_MIN_BLOCKS) k_env_step(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v,
                                                       const __grid_constant__ EnvStepDev<T> a) {
-  const int e_raw = blockIdx.x * kBlock + threadIdx.x;
+  const int e_raw = blockIdx.x * block_threads(MODE) + threadIdx.x;
   const bool active = e_raw < v.n;   // inactive lanes shadow the last env (they must reach the barriers)
   const int e = active ? e_raw : v.n - 1;
   T q[kNV], qd[kNV], w[kNV], act[7], u[kNU];
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(kBlock, CASSIE_MIN_BLOCKS) k_env_step(const __
   double t = v.clock[e];
   unsigned qps = v.qp_set[e];
   for (int s = 0; s < a.n_sub; s++) {
-    step_barrier();
+    step_barrier<block_threads(MODE)>();
     controller_step<MODE>(mp.phys, mp.phys_d, ctrl_model<MODE>(mp), mp.ctrl_d, q, qd, w, act, rows, u, s == a.n_sub - 1 ? &op : nullptr, &st, &qs, &qps);
     t += 0.0005;  // cassie2d.py:122
   }
@@ -243,9 +245,9 @@ __global__ void __launch_bounds__(128) k_env_reset(const __grid_constant__ Model
 // ---------------------------------------------------------------------------------------
 // squatting.py:8-16 with standing_controller_jacobian / standing_controller_osc in the loop
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kBlock, CASSIE_MIN_BLOCKS) k_squat(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v,
+__global__ void __launch_bounds__(block_threads(MODE), CASSIE_MIN_BLOCKS) k_squat(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v,
                                                    const T* __restrict__ phase, int n_steps, uint32_t* mask) {
-  const int e_raw = blockIdx.x * kBlock + threadIdx.x;
+  const int e_raw = blockIdx.x * block_threads(MODE) + threadIdx.x;
   const bool active = e_raw < v.n;   // inactive lanes shadow the last env (they must reach the barriers)
   const int e = active ? e_raw : v.n - 1;
   T q[kNV], qd[kNV], w[kNV], act[7], u[kNU];
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(kBlock, CASSIE_MIN_BLOCKS) k_squat(const __gri
   const double wq = 0.5 * 3.1415;  // squatting.py:9
   unsigned qps = v.qp_set[e];
   for (int s = 0; s < n_steps; s++) {
-    step_barrier();
+    step_barrier<block_threads(MODE)>();
     T o18[18];
     op_state_array(op, q, qd, o18);
     double sn, cs;
@@ -368,12 +370,13 @@ inline unsigned grid_for(int n, int block) { return (unsigned)((n + block - 1) /
 template <typename T>
 cudaError_t Launch<T>::step(const ModelPair<T>& mp, const BatchView<T>& v, const StepArgs& a, cudaStream_t s) {
   const T* act = (const T*)a.action;
-  const unsigned g = grid_for(v.n, kBlock);
+  const int bt = block_threads(a.mode);
+  const unsigned g = grid_for(v.n, bt);
   switch (a.mode) {
-    case kModeTorque: k_step<T, kModeTorque><<<g, kBlock, 0, s>>>(mp, v, act, a.n_substeps, a.contact_mask); break;
-    case kModePd: k_step<T, kModePd><<<g, kBlock, 0, s>>>(mp, v, act, a.n_substeps, a.contact_mask); break;
-    case kModeJacobian: k_step<T, kModeJacobian><<<g, kBlock, 0, s>>>(mp, v, act, a.n_substeps, a.contact_mask); break;
-    case kModeOsc: k_step<T, kModeOsc><<<g, kBlock, 0, s>>>(mp, v, act, a.n_substeps, a.contact_mask); break;
+    case kModeTorque: k_step<T, kModeTorque><<<g, bt, 0, s>>>(mp, v, act, a.n_substeps, a.contact_mask); break;
+    case kModePd: k_step<T, kModePd><<<g, bt, 0, s>>>(mp, v, act, a.n_substeps, a.contact_mask); break;
+    case kModeJacobian: k_step<T, kModeJacobian><<<g, bt, 0, s>>>(mp, v, act, a.n_substeps, a.contact_mask); break;
+    case kModeOsc: k_step<T, kModeOsc><<<g, bt, 0, s>>>(mp, v, act, a.n_substeps, a.contact_mask); break;
     default: return cudaErrorInvalidValue;
   }
   count_launch();
@@ -390,11 +393,12 @@ cudaError_t Launch<T>::env_step(const ModelPair<T>& mp, const BatchView<T>& v, c
                          0.0, 0.0, 0.0, 0.0, 0.0, 0.68111815, -1.40730357, 1.62972042, -1.77611107, -0.61968407,
                          0.0, 0.0, 0.0, 0.0, 0.0};
   for (int i = 0; i < 26; i++) d.reset_state[i] = (T)qi[i];
-  const unsigned g = grid_for(v.n, kBlock);
+  const int bt = block_threads(a.mode);
+  const unsigned g = grid_for(v.n, bt);
   switch (a.mode) {
-    case kModeTorque: k_env_step<T, kModeTorque><<<g, kBlock, 0, s>>>(mp, v, d); break;
-    case kModePd: k_env_step<T, kModePd><<<g, kBlock, 0, s>>>(mp, v, d); break;
-    case kModeOsc: k_env_step<T, kModeOsc><<<g, kBlock, 0, s>>>(mp, v, d); break;
+    case kModeTorque: k_env_step<T, kModeTorque><<<g, bt, 0, s>>>(mp, v, d); break;
+    case kModePd: k_env_step<T, kModePd><<<g, bt, 0, s>>>(mp, v, d); break;
+    case kModeOsc: k_env_step<T, kModeOsc><<<g, bt, 0, s>>>(mp, v, d); break;
     default: return cudaErrorInvalidValue;  // the Python envs have no Jacobian action space
   }
   count_launch();
@@ -403,9 +407,10 @@ cudaError_t Launch<T>::env_step(const ModelPair<T>& mp, const BatchView<T>& v, c
 
 template <typename T>
 cudaError_t Launch<T>::squat(const ModelPair<T>& mp, const BatchView<T>& v, const SquatArgs& a, cudaStream_t s) {
-  const unsigned g = grid_for(v.n, kBlock);
-  if (a.mode == kModeJacobian) k_squat<T, kModeJacobian><<<g, kBlock, 0, s>>>(mp, v, (const T*)a.phase, a.n_steps, a.contact_mask);
-  else if (a.mode == kModeOsc) k_squat<T, kModeOsc><<<g, kBlock, 0, s>>>(mp, v, (const T*)a.phase, a.n_steps, a.contact_mask);
+  const int bt = block_threads(a.mode);
+  const unsigned g = grid_for(v.n, bt);
+  if (a.mode == kModeJacobian) k_squat<T, kModeJacobian><<<g, bt, 0, s>>>(mp, v, (const T*)a.phase, a.n_steps, a.contact_mask);
+  else if (a.mode == kModeOsc) k_squat<T, kModeOsc><<<g, bt, 0, s>>>(mp, v, (const T*)a.phase, a.n_steps, a.contact_mask);
   else return cudaErrorInvalidValue;
   count_launch();
   return cudaGetLastError();
