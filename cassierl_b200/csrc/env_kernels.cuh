@@ -22,7 +22,10 @@ constexpr int kBlock = CASSIE_BLOCK;
 // instruction-cache fills (instruction fetch is the top stall of the step kernels).
 // The OSC kernels run one warp per CTA instead: they are bound by the L1 hit rate of the controller's thread-local
 // arrays, and 512 single-warp CTAs spread more evenly over the 148 SMs (3-4 warps each instead of 2-4): +2.5 %.
-constexpr int block_threads(int mode) { return mode == kModeOsc ? 32 : kBlock; }
+#ifndef CASSIE_OSC_BLOCK
+#define CASSIE_OSC_BLOCK 32
+#endif
+constexpr int block_threads(int mode) { return mode == kModeOsc ? CASSIE_OSC_BLOCK : kBlock; }
 template <int B>
 __device__ __forceinline__ void step_barrier() {
   if constexpr (B > 32) __syncthreads();
