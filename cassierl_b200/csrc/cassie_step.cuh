@@ -64,7 +64,15 @@ CASSIE_HD void controller_step(const PlanarModel<T>& mp, const PlanarModel<TG>& 
       CASSIE_UNROLL
       for (int i = 0; i < action_dim(MODE); i++) ac[i] = (TC)act[i];
       if (MODE == kModeJacobian) jacobian_control(mc, kc, qdc, ac, uc);
-      else osc_control(mc, kc, qdc, ac, uc, qst, qp_set);
+      else {
+#if defined(__CUDA_ARCH__) && !defined(CASSIE_NO_OSC_OVERLAY)
+        static_assert(sizeof(Rows<T>) >= kOscWsDoubles * sizeof(double), "constraint rows too small to host the QP scratch");
+        osc_control(mc, kc, qdc, ac, uc, qst, qp_set, reinterpret_cast<double*>(&rows));
+        asm volatile("" ::: "memory");  // the rows are re-typed below: no reordering of the physics stores above this
+#else
+        osc_control(mc, kc, qdc, ac, uc, qst, qp_set);
+#endif
+      }
       CASSIE_UNROLL
       for (int i = 0; i < kNU; i++) u[i] = (T)uc[i];
     }

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(block_threads(MODE), CASSIE_MIN_BLOCKS) k_step
   constexpr int adim = action_dim(MODE);
 #pragma unroll
   for (int i = 0; i < adim; i++) act[i] = action[(size_t)e * adim + i];
-  Rows<T> rows;
+  alignas(16) Rows<T> rows;
   OpState<T> op;
   StepStats st = {0, 0, 0u};
   OscStats qs = {0, 0};
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(block_threads(MODE), CASSIE_MIN_BLOCKS) k_env_
   constexpr int adim = action_dim(MODE);
 #pragma unroll
   for (int i = 0; i < adim; i++) act[i] = a.action[(size_t)e * adim + i];
-  Rows<T> rows;
+  alignas(16) Rows<T> rows;
   OpState<T> op;
   StepStats st = {0, 0, 0u};
   OscStats qs = {0, 0};
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(block_threads(MODE), CASSIE_MIN_BLOCKS) k_squa
   const int e = active ? e_raw : v.n - 1;
   T q[kNV], qd[kNV], w[kNV], act[7], u[kNU];
   load_env(v, e, q, qd, w);
-  Rows<T> rows;
+  alignas(16) Rows<T> rows;
   OpState<T> op;
   load_op(v, e, op);
   StepStats st = {0, 0, 0u};

@@ -39,12 +39,19 @@ constexpr double kOscWCom = 5.0, kOscWStance = 10.0, kOscWRest = 0.1, kOscWForce
 CASSIE_HD constexpr int qtri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
 constexpr int kQpTri = kQpN * (kQpN + 1) / 2;
 constexpr int kQpGreedyIters = 60;
+constexpr int kOscWsDoubles = (kQpTasks + 1) * kQpN + 2 * kQpTri;   // E, G, L
 
 // G and the Cholesky factor are packed lower triangles (105 entries): half the thread-local lines.
 CASSIE_HD void box_qp_solve(const double G[kQpTri], const double g[kQpN], const double lo[kQpN],
                             const double hi[kQpN], double z[kQpN], unsigned& at_lo, unsigned& at_hi, int max_iter,
-                            OscStats* st) {
-  double L[kQpTri], grad[kQpN], invd[kQpN];  // invd = 1 / L_ii: one division per pivot instead of one per entry
+                            OscStats* st, double* Lws = nullptr) {
+  double grad[kQpN], invd[kQpN];  // invd = 1 / L_ii: one division per pivot instead of one per entry
+#if defined(__CUDA_ARCH__) && !defined(CASSIE_NO_OSC_OVERLAY)
+  double* const L = Lws;
+#else
+  double Lloc[kQpTri];
+  double* const L = Lws ? Lws : Lloc;
+#endif
   double gscale = 1.0;
   for (int i = 0; i < kQpN; i++) gscale = fmax(gscale, fabs(g[i]));
   const double dtol = 1e-12 * gscale;
@@ -147,7 +154,7 @@ CASSIE_HD void box_qp_solve(const double G[kQpTri], const double g[kQpN], const 
 // body_xdd[2], left_xdd[2], right_xdd[2], pitch_add  (x, z pairs; Cassie2d.cpp:185-193).
 template <typename T>
 CASSIE_HD void osc_control(const PlanarModel<T>& m, const Kin<T>& k, const T* qd, const T act[7], T u[kNU], OscStats* st,
-                            unsigned* qp_set = nullptr) {
+                            unsigned* qp_set = nullptr, double* ws = nullptr) {
   CtrlDyn<T> d;
   ctrl_dynamics(m, k, qd, d);
   PivotAcc<T> pa;
@@ -189,7 +196,20 @@ CASSIE_HD void osc_control(const PlanarModel<T>& m, const Kin<T>& k, const T* qd
   // dots with the site Jacobians, which ARE task rows 2..9.  P = Mc^-1 B is never formed; E (11 x 14) is
   // stored once and  G = 2 E'WE,  g = 2 E'W r0  (OSC_RBDL.cpp:186-203) are then built entry by entry.
   //   r0_r = Jdot qd_r - xdd*_r + A_r p0,   A_r p0 = -Z_r . bias - (JH A_r') . (S^+ JdQd)
-  double E[kQpTasks + 1][kQpN], r0v[kQpTasks + 1];
+  // E, G and L may live in caller-provided scratch `ws` (kOscWsDoubles doubles): the kernels pass the storage of the
+  // physics step's constraint rows, which is dead while the controller runs, so that the two phases touch the
+  // same thread-local lines instead of two disjoint sets (the controller is bound by L1 / L2 hits)
+  double r0v[kQpTasks + 1];
+#if defined(__CUDA_ARCH__) && !defined(CASSIE_NO_OSC_OVERLAY)
+  double (*const E)[kQpN] = reinterpret_cast<double (*)[kQpN]>(ws);
+  double* const G = ws + (kQpTasks + 1) * kQpN;
+  double* const Lws = G + kQpTri;
+#else
+  double Eloc[kQpTasks + 1][kQpN], Gloc[kQpTri];
+  double (*const E)[kQpN] = ws ? reinterpret_cast<double (*)[kQpN]>(ws) : Eloc;
+  double* const G = ws ? ws + (kQpTasks + 1) * kQpN : Gloc;
+  double* const Lws = ws ? G + kQpTri : nullptr;
+#endif
   CASSIE_UNROLL
   for (int c = 0; c < 8; c++) A[kQpTasks][c] = T(0);   // padding task: the loop below handles two tasks per
   e0[kQpTasks] = T(0); aleg[kQpTasks] = 0;              // iteration so that every load of JH / T1 / LD serves both
@@ -239,7 +259,7 @@ CASSIE_HD void osc_control(const PlanarModel<T>& m, const Kin<T>& k, const T* qd
   // G = 2 E'WE (packed lower triangle, one store per entry), g = 2 E'W r0.  Two rows of G per pass: the
   // weighted columns i, i+1 of E sit in registers, every column j <= i+1 is loaded once and feeds four
   // independent accumulation chains.
-  double G[kQpTri], g[kQpN], lo[kQpN], hi[kQpN], z[kQpN];
+  double g[kQpN], lo[kQpN], hi[kQpN], z[kQpN];
   CASSIE_ROLL
   for (int i = 0; i < kQpN; i += 2) {
     double c0[kQpTasks], c1[kQpTasks];
@@ -273,7 +293,7 @@ CASSIE_HD void osc_control(const PlanarModel<T>& m, const Kin<T>& k, const T* qd
   for (int a = 0; a < kNU; a++) { lo[a] = (double)m.act_lo[a]; hi[a] = (double)m.act_hi[a]; }
   for (int i = kNU; i < kQpN; i++) { lo[i] = 0.0; hi[i] = 1e30; }
   unsigned at_lo = qp_set ? (*qp_set & 0x3fffu) : 0u, at_hi = qp_set ? ((*qp_set >> 14) & 0x3fu) : 0u;
-  box_qp_solve(G, g, lo, hi, z, at_lo, at_hi, 300, st);
+  box_qp_solve(G, g, lo, hi, z, at_lo, at_hi, 300, st, Lws);
   if (qp_set) *qp_set = at_lo | (at_hi << 14);
   CASSIE_UNROLL
   for (int a = 0; a < kNU; a++) u[a] = (T)z[a];

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kBlock, CASSIE_MIN_BLOCKS) k_rollout(const __g
   if (e >= v.n) return;
   T q[kNV], qd[kNV], w[kNV], u[kNU];
   load_env(v, e, q, qd, w);
-  Rows<T> rows;
+  alignas(16) Rows<T> rows;
   OpState<T> op;
   load_op(v, e, op);
   StepStats st = {0, 0, 0u};
