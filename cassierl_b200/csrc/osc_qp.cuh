@@ -155,7 +155,11 @@ CASSIE_HD void box_qp_solve(const double G[kQpTri], const double g[kQpN], const 
 template <typename T>
 CASSIE_HD void osc_control(const PlanarModel<T>& m, const Kin<T>& k, const T* qd, const T act[7], T u[kNU], OscStats* st,
                             unsigned* qp_set = nullptr, double* ws = nullptr) {
+#if defined(__CUDA_ARCH__) && !defined(CASSIE_NO_OSC_OVERLAY)
+  CtrlDyn<T>& d = *reinterpret_cast<CtrlDyn<T>*>(ws + kOscWsDoubles);
+#else
   CtrlDyn<T> d;
+#endif
   ctrl_dynamics(m, k, qd, d);
   PivotAcc<T> pa;
   pivot_accelerations(k, pa);
@@ -196,9 +200,10 @@ CASSIE_HD void osc_control(const PlanarModel<T>& m, const Kin<T>& k, const T* qd
   // dots with the site Jacobians, which ARE task rows 2..9.  P = Mc^-1 B is never formed; E (11 x 14) is
   // stored once and  G = 2 E'WE,  g = 2 E'W r0  (OSC_RBDL.cpp:186-203) are then built entry by entry.
   //   r0_r = Jdot qd_r - xdd*_r + A_r p0,   A_r p0 = -Z_r . bias - (JH A_r') . (S^+ JdQd)
-  // E, G and L may live in caller-provided scratch `ws` (kOscWsDoubles doubles): the kernels pass the storage of the
-  // physics step's constraint rows, which is dead while the controller runs, so that the two phases touch the
-  // same thread-local lines instead of two disjoint sets (the controller is bound by L1 / L2 hits)
+  // E, G, L (and CtrlDyn above) live in caller-provided scratch `ws`: the kernels pass the storage of the physics
+  // step's constraint rows, which is dead while the controller runs, so that the two phases touch the same
+  // thread-local lines instead of two disjoint sets (the controller is bound by L1 / L2 hits, DESIGN.md 5:
+  // E/G/L +1 %, CtrlDyn another +4 %; the task Jacobians A on top of that lost 2 % again)
   double r0v[kQpTasks + 1];
 #if defined(__CUDA_ARCH__) && !defined(CASSIE_NO_OSC_OVERLAY)
   double (*const E)[kQpN] = reinterpret_cast<double (*)[kQpN]>(ws);
