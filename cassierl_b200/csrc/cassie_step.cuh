@@ -66,7 +66,7 @@ CASSIE_HD void controller_step(const PlanarModel<T>& mp, const PlanarModel<TG>& 
       if (MODE == kModeJacobian) jacobian_control(mc, kc, qdc, ac, uc);
       else {
 #if defined(__CUDA_ARCH__) && !defined(CASSIE_NO_OSC_OVERLAY)
-        static_assert(sizeof(Rows<T>) >= kOscWsDoubles * sizeof(double) + sizeof(CtrlDyn<TC>), "constraint rows too small to host the QP scratch");
+        static_assert(sizeof(Rows<T>) >= kOscWsDoubles * sizeof(double) + sizeof(CtrlDyn<TC>) + 4 * kQpN * sizeof(double), "constraint rows too small to host the QP scratch");
         osc_control(mc, kc, qdc, ac, uc, qst, qp_set, reinterpret_cast<double*>(&rows));
         asm volatile("" ::: "memory");  // the rows are re-typed below: no reordering of the physics stores above this
 #else
