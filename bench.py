@@ -47,6 +47,8 @@ WORKLOADS = {
     "pd_env": "cassie2d_stiff.xml, cassie_stand2d env step (StepPd x10 + obs/reward/done + auto-reset)",
 }
 DEFAULT_WORKLOAD = "squat_osc"   # BASELINE.json configs[2]: 16384 envs, OSC_RBDL squatting controller in the loop
+METRIC = "env-steps/sec cassie2d_stiff @16k envs"   # the SAME string on both arms (the driver divides one by the other)
+MODE_OF = {"squat_jacobian": 2, "squat_osc": 3, "torque_random": 0, "pd_env": 1}
 
 
 def parse():
@@ -61,7 +63,22 @@ def parse():
     p.add_argument("--precision", type=int, default=32, choices=[32, 64])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=10.0)
+    p.add_argument("--preadvance", type=int, default=1000,
+                   help="simulator steps every env is advanced OUTSIDE the timed region (steady state, not the start-up transient)")
+    p.add_argument("--ref-envs", type=int, default=1024, help="--impl reference: envs of the bounded CPU sample")
     return p.parse_args()
+
+
+def kernel_source_hash():
+    """sha256 over the CUDA sources of the step path: profiles/traffic.json entries carry the hash of the
+    sources their ncu capture ran, and bench.py prints `roofline.traffic` only while it still matches."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "cassierl_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cuh", ".cu", ".h")):
+            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle)
@@ -91,40 +108,84 @@ def oracle_rate(workload, n_envs, n_steps, threads, seed=1):
     return n / dt, dt
 
 
-def cpu_baseline(workload, seconds):
+def cpu_baseline(workload, seconds, preadvance=1000):
+    """The oracle port timed on this box's host cores: a bounded sample of the same workload, persistent envs
+    pre-advanced like the native arm's (steady state), ~`seconds` of CPU work."""
+    from oracle import oracle as O
     cores = os.cpu_count() or 1
     rate, _ = oracle_rate(workload, cores, 50, cores)            # calibration
     n_envs = cores * 4
+    mode = MODE_OF[workload]
+    pool = O.Pool(oracle_rate.model, n_envs)
+    phase = 2 * np.pi * np.arange(n_envs) / n_envs
+    rng = np.random.default_rng(1)
+    hi = np.array([12.0, 12.0, 0.9, 12.0, 12.0, 0.9])
+    lo_pd = np.radians([-50.0, -164.0, -140.0, -50.0, -164.0, -140.0]); hi_pd = np.radians([80.0, -37.0, -30.0, 80.0, -37.0, -30.0])
+
+    def run(n_steps):
+        if mode >= 2:
+            return pool.run(n_steps, mode, phase=phase, n_threads=cores)[0]
+        nact = (n_steps + 9) // 10
+        a = rng.uniform(-1, 1, (n_envs, nact, 6)) * hi if mode == 0 else rng.uniform(lo_pd, hi_pd, (n_envs, nact, 6))
+        return pool.run(n_steps, mode, actions=a, hold=10, n_threads=cores)[0]
+
+    run(preadvance)
     n_steps = int(max(50, min(20000, rate * seconds / n_envs)))
-    rate, dt = oracle_rate(workload, n_envs, n_steps, cores)
-    return {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
-            "sample": "%d envs x %d sim steps of the same workload, fp64 oracle (oracle/, gcc -O3 -fopenmp), %.1f s" % (n_envs, n_steps, dt)}
+    t0 = time.perf_counter()
+    n = run(n_steps)
+    dt = time.perf_counter() - t0
+    pool.close()
+    return {"value": n / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
+            "sample": "%d persistent envs x %d sim steps of the same workload after %d pre-advance steps, fp64 oracle (oracle/, gcc -O3 -fopenmp), %.1f s"
+                      % (n_envs, n_steps, preadvance, dt)}
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path cannot be built here (MuJoCo
-    1.50 / RBDL / qpOASES absent), so this times the oracle port on all host cores."""
+    1.50 / RBDL / qpOASES absent), so this times the oracle port on all host cores.  The envs are PERSISTENT
+    (oracle.Pool): facades, QP hot start and squat clocks live across the bench steps, exactly like the native
+    arm's device state, and they are pre-advanced by the same --preadvance simulator steps before timing."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import oracle as O
+    O.build()
     cores = os.cpu_count() or 1
-    n_envs = 1024                                # bounded sample of the 16384-env workload
+    n_envs, sub, wl = args.ref_envs, args.substeps, args.workload     # bounded sample of the 16384-env workload
+    mode = MODE_OF[wl]
+    pool = O.Pool(O.Model(), n_envs)
+    phase = 2 * np.pi * np.arange(n_envs) / max(n_envs, 1)
+    rng = np.random.default_rng(1)
+    hi = np.array([12.0, 12.0, 0.9, 12.0, 12.0, 0.9])
+    lo_pd = np.radians([-50.0, -164.0, -140.0, -50.0, -164.0, -140.0]); hi_pd = np.radians([80.0, -37.0, -30.0, 80.0, -37.0, -30.0])
+
+    def one(n_steps):
+        if mode >= 2:
+            return pool.run(n_steps, mode, phase=phase, n_threads=cores)[0]
+        nact = (n_steps + 9) // 10
+        a = rng.uniform(-1, 1, (n_envs, nact, 6)) * hi if mode == 0 else rng.uniform(lo_pd, hi_pd, (n_envs, nact, 6))
+        return pool.run(n_steps, mode, actions=a, hold=10, n_threads=cores)[0]
+
+    if args.preadvance > 0:
+        one(args.preadvance)
     for _ in range(args.warmup):
-        oracle_rate(args.workload, n_envs, args.substeps, cores)
+        one(sub)
     t0 = time.perf_counter()
     total = 0
     for _ in range(args.steps):
-        r, dt = oracle_rate(args.workload, n_envs, args.substeps, cores)
-        total += n_envs * args.substeps
+        total += one(sub)
     el = time.perf_counter() - t0
+    pool.close()
     v = total / el
-    line = {"impl": "reference", "metric": "env-steps/sec cassie2d_stiff", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
+    sample = "%d persistent envs x %d sim steps per step, %d steps, pre-advanced %d sim steps; fp64 oracle port, OpenMP over envs" % (
+        n_envs, sub, args.steps, args.preadvance)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "envs_per_step_sample": n_envs, "substeps": args.substeps,
+            "config": {"workload": WORKLOADS[wl], "workload_key": wl, "envs_per_step_sample": n_envs, "substeps": sub,
+                       "preadvance_sim_steps": args.preadvance,
                        "note": "CPU restatement (oracle port) of MuJoCo+RBDL path; the reference itself is unbuildable here"},
-            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                             "sample": "%d envs x %d sim steps per step, %d steps" % (n_envs, args.substeps, args.steps)},
+            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -241,7 +302,8 @@ def run_native(args):
     phase = (2 * np.pi * ((gid0 + np.arange(n)) % n) / n).astype(np.float64)
     gen = np.random.default_rng(1 + rank)
     hi = np.array([12.0, 12.0, 0.9, 12.0, 12.0, 0.9])
-    total_steps = args.warmup + args.steps
+    n_pre = (args.preadvance + sub - 1) // sub if sub > 0 else 0   # launches that advance every env OUTSIDE the timed region
+    total_steps = n_pre + args.warmup + args.steps
 
     def make():
         if wl == "pd_env":
@@ -275,9 +337,19 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for k in range(args.warmup):
+    def solver_stats_of(batch):
+        st = batch.stats().double()
+        return {"rows_mean": float(st[:, 0].mean().item()), "rows_max": int(st[:, 0].max().item()),
+                "pgs_sweeps_mean": float(st[:, 1].mean().item()), "qp_iters_mean": float(st[:, 2].mean().item()),
+                "qp_not_optimal": int((st[:, 3] != 0).sum().item())}
+
+    # steady state, not the start-up transient: every env is advanced >= --preadvance simulator steps first
+    for k in range(n_pre):
         one_step(k)
+    for k in range(args.warmup):
+        one_step(n_pre + k)
     barrier()
+    stats_start = solver_stats_of(b)
     try:
         uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
     except Exception:
@@ -291,7 +363,7 @@ def run_native(args):
     for k in range(args.steps):
         flush.zero_()                                   # L2 flush, outside the timed events
         ev[k][0].record()
-        one_step(args.warmup + k)
+        one_step(n_pre + args.warmup + k)
         ev[k][1].record()
     barrier()
     launches = L.CassieKernelLaunchCount() - launches0
@@ -308,10 +380,7 @@ def run_native(args):
         dist.all_reduce(stats)
     # constraint rows / PGS sweeps / QP iterations of the LAST sim step (rank 0's shard): which solver tier the
     # workload sits in at the end of the timed window (<= 8 rows narrow, <= 12 wide register path, more = cold path)
-    st = b.stats().double()
-    solver_stats = {"rows_mean": float(st[:, 0].mean().item()), "rows_max": int(st[:, 0].max().item()),
-                    "pgs_sweeps_mean": float(st[:, 1].mean().item()), "qp_iters_mean": float(st[:, 2].mean().item()),
-                    "qp_not_optimal": int((st[:, 3] != 0).sum().item())}
+    solver_stats = solver_stats_of(b)
     value = world * n * sub * args.steps / (ms_max * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI entry points (pinned host memory in and out)
@@ -335,12 +404,21 @@ def run_native(args):
             b2.step_host(lib.MODE_TORQUE, acts_h[k], sub, st_h); return n * 6 * rs, n * 26 * rs
         obj2.step_host(acts_h[k], obs_h, rew_h, done_h, n=sub); return n * 6 * rs, n * (17 * rs + rs + 1)
 
+    for k in range(n_pre):                                    # same steady state as the device-timed leg
+        if wl == "squat_jacobian":
+            b2.squat(lib.MODE_JACOBIAN, sub, phase=phase_d)
+        elif wl == "squat_osc":
+            b2.squat(lib.MODE_OSC, sub, phase=phase_d)
+        elif wl == "torque_random":
+            b2.step_torque(acts[k], sub)
+        else:
+            obj2.step(acts[k], n=sub)
     for k in range(args.warmup):
-        h2d, d2h = one_e2e(k)
+        h2d, d2h = one_e2e(n_pre + k)
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        one_e2e(args.warmup + k)
+        one_e2e(n_pre + args.warmup + k)
     torch.cuda.synchronize()
     el = time.perf_counter() - t0
     t = torch.tensor([el], dtype=torch.float64, device=dev)
@@ -367,14 +445,15 @@ def run_native(args):
         bytes_launch = n * (STATE_BYTES_PER_ENV_F32 * rs // 4 + rs)
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         line = {
-            "metric": "env-steps/sec cassie2d_stiff @16k envs", "value": value, "unit": "env-steps/s", "n_gpus": world,
+            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_launch, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[wl], "workload_key": wl, "envs_per_gpu": n, "sim_steps_per_launch": sub,
-                       "policy_steps_per_s": value / sub, "l2": "flushed between timed steps (256 MiB memset)",
+                       "policy_steps_per_s": value / sub, "preadvance_sim_steps": n_pre * sub,
+                       "l2": "flushed between timed steps (256 MiB memset)",
                        "parallelism": "env-sharded dp%d, no data-path collective" % world},
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp32_peak if fp32_peak > 0 else None, "traffic": traffic,
+                         "frac": achieved / fp32_peak if fp32_peak > 0 else None, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": "measured live: register-only FFMA kernel (CassieMeasureFp32Peak); MEASURED_PEAKS.json has no FP32 figure",
                          "flops_per_env_step": fl, "kernel_ms": ms_launch,
                          "hbm": {"achieved_gbs": bytes_launch / (ms_launch * 1e-3) / 1e9, "peak_gbs": hbm_peak,
@@ -383,10 +462,10 @@ def run_native(args):
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks,
             "stats": {"mean_pelvis_z": float(stats[0].item()) / (n * world), "envs_below_0.5m": int(stats[1].item()),
-                      "non_finite_envs": int(stats[2].item()), "last_step": solver_stats},
+                      "non_finite_envs": int(stats[2].item()), "first_timed_step": stats_start, "last_step": solver_stats},
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(wl, args.cpu_seconds)
+            line["cpu_baseline"] = cpu_baseline(wl, args.cpu_seconds, args.preadvance)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

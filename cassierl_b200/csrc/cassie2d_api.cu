@@ -374,6 +374,14 @@ int Cassie2dBatchGetStats(CassieBatch* h, int32_t* stats_dev, void* stream) {
   return 0;
 }
 
+int Cassie2dBatchGetEpisodeLengths(CassieBatch* h, int32_t* ep_len_dev, void* stream) {
+  if (!h || !ep_len_dev) return fail("null argument");
+  if (set_device(h)) return -1;
+  const int32_t* src = h->precision == 64 ? h->v64.ep_len : h->v32.ep_len;
+  CU_OK(cudaMemcpyAsync(ep_len_dev, src, sizeof(int32_t) * (size_t)h->n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
 int Cassie2dBatchSetWarmStart(CassieBatch* h, const void* qacc_dev, void* stream) {
   if (!h || !qacc_dev) return fail("null argument");
   if (set_device(h)) return -1;

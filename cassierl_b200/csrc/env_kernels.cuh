@@ -138,8 +138,11 @@ __device__ __forceinline__ int traj_index(double t, double tmax, int rows) {
   return i < rows ? i : rows - 1;
 }
 
+// zero_ref: the observation env.reset() returns has zeros in its reference slots 17..25 (cassie2d.py:78-95 returns
+// operational_state_array_to_pos_invariant_array(s), cassie2d_structs.py:68-75; only step() fills them, :158-166)
 template <typename T>
-__device__ __forceinline__ void write_obs(const BatchView<T>& v, int task, int e, const T o18[18], double t, T* obs, T ref9[9]) {
+__device__ __forceinline__ void write_obs(const BatchView<T>& v, int task, int e, const T o18[18], double t, T* obs, T ref9[9],
+                                          bool zero_ref = false) {
   T o[17];
   pos_invariant_obs(o18, o);
   if (task == kTaskStand) {
@@ -153,7 +156,72 @@ __device__ __forceinline__ void write_obs(const BatchView<T>& v, int task, int e
 #pragma unroll
     for (int i = 0; i < 9; i++) {
       ref9[i] = v.traj ? (T)v.traj[(size_t)row * 13 + idx9[i]] : T(0);
-      obs[(size_t)e * 26 + 17 + i] = ref9[i];
+      obs[(size_t)e * 26 + 17 + i] = zero_ref ? T(0) : ref9[i];
+    }
+  }
+}
+
+// mj_checkPos / mj_checkVel / mj_checkAcc [EXT]: MuJoCo resets the data when the state is not finite or has left
+// any sane range.  A NaN env would otherwise never report done (every comparison with NaN is false) and would
+// poison the batch statistics; here it is reported done, reset, and flagged in stats[3] (kStatusDiverged).
+constexpr int kStatusDiverged = 3;
+template <typename T>
+__device__ __forceinline__ bool state_diverged(const T q[kNV], const T qd[kNV]) {
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < kNV; i++) bad = bad || !(Num<T>::abs_(q[i]) < T(1e10)) || !(Num<T>::abs_(qd[i]) < T(1e10));
+  return bad;
+}
+
+// The part of Cassie2dEnv.step() after the n substeps (cassie_stand2d.py:104-137 / cassie2d.py:124-225) plus the
+// batch conventions: observation, reward, termination, divergence guard, auto-reset.  One env; called by one lane.
+//   flags: CASSIE_AUTO_RESET 1, CASSIE_FRESH_OBS_ON_RESET 2, CASSIE_LIVE_QSTATE 4, CASSIE_TERMINAL_OBS 8.
+// With auto-reset the observation returned for a done env is the one env.reset() returns (the caller's next action
+// must see the new episode), unless CASSIE_TERMINAL_OBS asks for the terminal one.
+template <typename T>
+__device__ __forceinline__ void env_finish(const ModelPair<T>& mp, const BatchView<T>& v, int task, int flags, int e,
+                                           T q[kNV], T qd[kNV], T w[kNV], OpState<T>& op, double& t, unsigned& qps,
+                                           const T* act, int adim, const T reset_state[26], T* obs_out, T* rew_out,
+                                           uint8_t* done_out, OscStats& qs) {
+  const bool diverged = state_diverged(q, qd);
+  T o18[18], ref9[9], r;
+  int done;
+  op_state_array(op, q, qd, o18);
+  if (diverged) {
+#pragma unroll
+    for (int i = 0; i < 18; i++) o18[i] = T(0);
+  }
+  write_obs(v, task, e, o18, t, obs_out, ref9);
+  if (task == kTaskStand) {
+    T o[17];
+    pos_invariant_obs(o18, o);
+    stand_reward(o18, o, act, adim, r, done);
+  } else {
+    const T jsum = (flags & 4) ? q[3] + q[4] + q[6] + q[8] + q[9] + q[11] : v.jsum0[e];
+    imitate_reward(o18, ref9, jsum, r, done);
+  }
+  if (diverged) { r = T(0); done = 1; qs.status = kStatusDiverged; }
+  rew_out[e] = r;
+  done_out[e] = (uint8_t)done;
+  if ((done && (flags & 1)) || diverged) {
+    // env.reset(): Reset() + self.time = 0 (cassie2d.py:78-95).  Warm start and, unless
+    // CASSIE_FRESH_OBS_ON_RESET, the lagged op-space state survive (SURVEY App. D.2/D.3).
+    state26_to_q(reset_state, q, qd);
+    t = 0.0;
+    v.jsum0[e] = q[3] + q[4] + q[6] + q[8] + q[9] + q[11];
+    if ((flags & 2) || diverged) {
+      Kin<T> kc;
+      forward_kinematics(mp.ctrl, q, qd, kc);
+      op_state_from_kin(mp.ctrl, kc, q, op);
+    }
+    if (diverged) {   // mj_resetData [EXT]: the solver state goes too
+#pragma unroll
+      for (int i = 0; i < kNV; i++) w[i] = T(0);
+      qps = 0u;
+    }
+    if (!(flags & 8) || diverged) {
+      op_state_array(op, q, qd, o18);
+      write_obs(v, task, e, o18, 0.0, obs_out, ref9, true);
     }
   }
 }
@@ -182,32 +250,7 @@ __global__ void __launch_bounds__(block_threads(MODE), CASSIE_MIN_BLOCKS) k_env_
     t += 0.0005;  // cassie2d.py:122
   }
   if (!active) return;
-  T o18[18], ref9[9], r;
-  int done;
-  op_state_array(op, q, qd, o18);
-  write_obs(v, a.task, e, o18, t, a.obs, ref9);
-  if (a.task == kTaskStand) {
-    T o[17];
-    pos_invariant_obs(o18, o);
-    stand_reward(o18, o, act, adim, r, done);
-  } else {
-    const T jsum = (a.flags & 4) ? q[3] + q[4] + q[6] + q[8] + q[9] + q[11] : v.jsum0[e];
-    imitate_reward(o18, ref9, jsum, r, done);
-  }
-  a.reward[e] = r;
-  a.done[e] = (uint8_t)done;
-  if (done && (a.flags & 1)) {
-    // env.reset(): Reset() + self.time = 0 (cassie2d.py:78-95).  Warm start and, unless
-    // CASSIE_FRESH_OBS_ON_RESET, the lagged op-space state survive (SURVEY App. D.2/D.3).
-    state26_to_q(a.reset_state, q, qd);
-    t = 0.0;
-    v.jsum0[e] = q[3] + q[4] + q[6] + q[8] + q[9] + q[11];
-    if (a.flags & 2) {
-      Kin<T> kc;
-      forward_kinematics(mp.ctrl, q, qd, kc);
-      op_state_from_kin(mp.ctrl, kc, q, op);
-    }
-  }
+  env_finish(mp, v, a.task, a.flags, e, q, qd, w, op, t, qps, act, adim, a.reset_state, a.obs, a.reward, a.done, qs);
   v.clock[e] = t;
   v.qp_set[e] = qps;
   store_env(v, e, q, qd, w);
@@ -241,7 +284,7 @@ __global__ void __launch_bounds__(128) k_env_reset(const __grid_constant__ Model
   if (obs) {
     T o18[18], ref9[9];
     op_state_array(op, q, qd, o18);
-    write_obs(v, task, e, o18, 0.0, obs, ref9);
+    write_obs(v, task, e, o18, 0.0, obs, ref9, true);
   }
 }
 

@@ -90,12 +90,14 @@ __global__ void __launch_bounds__(kBlock, CASSIE_MIN_BLOCKS) k_rollout(const __g
   int ep_len = v.ep_len[e];
   uint32_t pstep = (uint32_t)v.policy_step[e];
   const size_t n = (size_t)v.n;
+  int n_diverged = 0;
 
   for (int k = 0; k < a.T_steps; k++) {
     // ---- observation of the current state (what the previous step / reset returned)
     T o18[18], ref9[9];
     op_state_array(op, q, qd, o18);
-    write_obs(v, a.task, e, o18, t, a.obs + (size_t)k * n * odim, ref9);
+    const bool fresh = ep_len == 0;   // the observation env.reset() returned: reference slots are zero (cassie2d.py:78-95)
+    write_obs(v, a.task, e, o18, t, a.obs + (size_t)k * n * odim, ref9, fresh);
     {
       T o[17];
       pos_invariant_obs(o18, o);
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(kBlock, CASSIE_MIN_BLOCKS) k_rollout(const __g
       for (int i = 0; i < 17; i++) sobs[i * kBlock + threadIdx.x] = o[i];
       if (a.task != kTaskStand) {
 #pragma unroll
-        for (int i = 0; i < 9; i++) sobs[(17 + i) * kBlock + threadIdx.x] = ref9[i];
+        for (int i = 0; i < 9; i++) sobs[(17 + i) * kBlock + threadIdx.x] = fresh ? T(0) : ref9[i];
       }
     }
     // ---- GaussianMLPPolicy forward: tanh hidden layers, linear mean head (trpo_cassie.py:21-27)
@@ -150,6 +152,7 @@ __global__ void __launch_bounds__(kBlock, CASSIE_MIN_BLOCKS) k_rollout(const __g
     }
     T r;
     int done;
+    const bool diverged = state_diverged(q, qd);   // mj_checkPos/Vel/Acc [EXT]: report done, reset, flag in stats
     op_state_array(op, q, qd, o18);
     if (a.task == kTaskStand) {
       T o[17];
@@ -163,6 +166,7 @@ __global__ void __launch_bounds__(kBlock, CASSIE_MIN_BLOCKS) k_rollout(const __g
       const T jsum = (a.flags & 4) ? q[3] + q[4] + q[6] + q[8] + q[9] + q[11] : v.jsum0[e];
       imitate_reward(o18, ref9, jsum, r, done);
     }
+    if (diverged) { r = T(0); done = 1; qs.status = kStatusDiverged; n_diverged++; }
     ep_len++;
     pstep++;
     int flag = done ? 1 : (ep_len >= a.max_path_length ? 2 : 0);
@@ -173,10 +177,15 @@ __global__ void __launch_bounds__(kBlock, CASSIE_MIN_BLOCKS) k_rollout(const __g
       t = 0.0;
       ep_len = 0;
       v.jsum0[e] = q[3] + q[4] + q[6] + q[8] + q[9] + q[11];
-      if (a.flags & 2) {
+      if ((a.flags & 2) || diverged) {
         Kin<T> kc;
         forward_kinematics(mp.ctrl, q, qd, kc);
         op_state_from_kin(mp.ctrl, kc, q, op);
+      }
+      if (diverged) {
+#pragma unroll
+        for (int i = 0; i < kNV; i++) w[i] = T(0);
+        qps = 0u;
       }
     }
   }
@@ -186,6 +195,7 @@ __global__ void __launch_bounds__(kBlock, CASSIE_MIN_BLOCKS) k_rollout(const __g
   v.policy_step[e] = (int32_t)pstep;
   store_env(v, e, q, qd, w);
   store_op(v, e, op);
+  if (n_diverged) qs.status = kStatusDiverged;   // sticky for the launch: the env diverged and was reset at least once
   store_stats(v.stats, v.n, e, st, qs);
 }
 

@@ -166,7 +166,7 @@ class Cassie2dBatchEnv:
     """
 
     def __init__(self, n_envs, device=0, task="stand", control_mode="OSC", precision=32, auto_reset=True,
-                 reference_faithful=True, trajectory=None):
+                 reference_faithful=True, trajectory=None, terminal_obs=False):
         self.batch = Cassie2dBatch(n_envs, device, precision)
         self.n = self.batch.n
         self.task = _lib.TASK_STAND if task == "stand" else _lib.TASK_IMITATE
@@ -177,6 +177,8 @@ class Cassie2dBatchEnv:
         self.flags = (_lib.AUTO_RESET if auto_reset else 0)
         if not reference_faithful:
             self.flags |= _lib.FRESH_OBS_ON_RESET | _lib.LIVE_QSTATE
+        if terminal_obs:   # auto-reset returns the terminal observation instead of the new episode's first one
+            self.flags |= _lib.TERMINAL_OBS
         if self.task == _lib.TASK_IMITATE:
             tr = trajectory if trajectory is not None else Cassie2dTraj()
             q = np.ascontiguousarray(tr.qpos, np.float64)
@@ -215,6 +217,10 @@ class Cassie2dBatchEnv:
         return self._obs
 
     def step(self, action, n=10):
+        """-> obs, reward, done.  With auto_reset a done env has already been reset when the call returns and its
+        obs is the one env.reset() gives (so the next action is computed for the new episode); terminal_obs=True
+        keeps the terminal observation instead.  An env whose state went non-finite reports done, reward 0, is
+        reset (solver state included) and shows status 3 in stats()[:, 3]."""
         b = self.batch
         a = b._t(action, self.action_dim)
         with torch.cuda.device(b.device):

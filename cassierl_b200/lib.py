@@ -11,7 +11,8 @@ LIB_PATH = os.environ.get("CASSIE2D_LIB") or os.path.join(_HERE, "lib", "libcass
 
 MODE_TORQUE, MODE_PD, MODE_JACOBIAN, MODE_OSC = 0, 1, 2, 3
 TASK_STAND, TASK_IMITATE = 0, 1
-AUTO_RESET, FRESH_OBS_ON_RESET, LIVE_QSTATE = 1, 2, 4
+AUTO_RESET, FRESH_OBS_ON_RESET, LIVE_QSTATE, TERMINAL_OBS = 1, 2, 4, 8
+STATUS_DIVERGED = 3
 F32, F64 = 32, 64
 
 # every symbol include/cassie2d.h declares
@@ -22,7 +23,7 @@ BATCH_SYMBOLS = ["CassieGetLastError", "Cassie2dBatchInit", "Cassie2dBatchDestro
                  "Cassie2dBatchSetState", "Cassie2dBatchGetGeneralState", "Cassie2dBatchGetOperationalSpaceState",
                  "Cassie2dBatchStep", "Cassie2dBatchEnvStep", "Cassie2dBatchEnvReset", "Cassie2dBatchSetTrajectory",
                  "Cassie2dBatchSquat", "Cassie2dBatchRollout", "Cassie2dBatchDiscountedReturns", "Cassie2dBatchBaselineMoments", "Cassie2dBatchAdvantages", "Cassie2dBatchStepHost", "Cassie2dBatchEnvStepHost", "Cassie2dBatchSquatHost",
-                 "Cassie2dBatchGetStats", "Cassie2dBatchSetWarmStart", "Cassie2dBatchGetWarmStart", "Cassie2dBatchSync", "CassieMeasureFp32Peak", "CassieKernelLaunchCount"]
+                 "Cassie2dBatchGetStats", "Cassie2dBatchGetEpisodeLengths", "Cassie2dBatchSetWarmStart", "Cassie2dBatchGetWarmStart", "Cassie2dBatchSync", "CassieMeasureFp32Peak", "CassieKernelLaunchCount"]
 
 _lib = None
 
@@ -62,6 +63,7 @@ def load():
     L.Cassie2dBatchSquatHost.argtypes = [vp, ci, ci, vp, vp]
     L.Cassie2dBatchGetStats.argtypes = [vp, vp, vp]
     L.Cassie2dBatchSetWarmStart.argtypes = [vp, vp, vp]
+    L.Cassie2dBatchGetEpisodeLengths.argtypes = [vp, vp, vp]
     L.Cassie2dBatchGetWarmStart.argtypes = [vp, vp, vp]
     L.CassieMeasureFp32Peak.restype = cd
     L.CassieMeasureFp32Peak.argtypes = [ci]

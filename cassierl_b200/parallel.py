@@ -31,15 +31,18 @@ def squat_phases(ids, n_total, dtype=torch.float32):
 class RolloutStats:
     """Running sums a learner wants from a rollout: reward, path length, episodes, non-finite envs."""
 
-    FIELDS = ("reward_sum", "steps", "episodes", "non_finite")
+    FIELDS = ("reward_sum", "steps", "episodes", "non_finite", "terminated", "truncated")
 
     def __init__(self, device="cpu"):
         self.acc = torch.zeros(len(self.FIELDS), dtype=torch.float64, device=device)
 
     def update(self, reward, done, obs=None):
+        """done: bool, or the rollout kernel's uint8 flag (1 = env terminated, 2 = max_path_length reached)"""
         self.acc[0] += reward.double().sum()
         self.acc[1] += reward.numel()
-        self.acc[2] += done.double().sum()
+        self.acc[2] += (done != 0).double().sum()
+        self.acc[4] += (done == 1).double().sum()
+        self.acc[5] += (done == 2).double().sum()
         if obs is not None:
             self.acc[3] += (~torch.isfinite(obs).all(dim=-1)).double().sum()
 

@@ -93,7 +93,12 @@ class RolloutCollector:
         self._buffers(T)
         b = self.batch
         p = policy.flat.to(dtype=b.dtype, device=b.device).contiguous()
+        # episodes continue across collect() calls: remember where each env's current path stands so that the
+        # baseline's time features (al, al^2, al^3) of the first path of this batch start at the right index
+        if getattr(self, "_path_start", None) is None:
+            self._path_start = torch.empty(b.n, dtype=torch.int32, device=b.device)
         with torch.cuda.device(b.device):
+            _lib.check(b.L.Cassie2dBatchGetEpisodeLengths(b.h, self._path_start.data_ptr(), _stream_ptr()), "GetEpisodeLengths")
             _lib.check(b.L.Cassie2dBatchRollout(
                 b.h, self.task, self.mode, p.data_ptr(), p.numel(), int(T), self.n_substeps, self.max_path_length, self.flags,
                 int(self.normalize), self.seed, self.env0, self.obs.data_ptr(), self.act.data_ptr(), self.mean.data_ptr(),
@@ -101,7 +106,9 @@ class RolloutCollector:
         return dict(observations=self.obs, actions=self.act, means=self.mean, rewards=self.rew, dones=self.done)
 
     def discounted_returns(self, gamma=0.99, tail=None):
-        """returns[T, N] of the last collect() (discount 0.99: trpo_cassie.py:38), on device"""
+        """returns[T, N] of the last collect() (discount 0.99: trpo_cassie.py:38), on device.  Paths still running
+        when the buffer ends are truncated there: they are bootstrapped with `tail` (real [N], e.g. the baseline's
+        value of the last observation) or with 0 when tail is None -- rllab's sampler truncates a batch the same way."""
         b = self.batch
         ret = torch.empty_like(self.rew)
         with torch.cuda.device(b.device):
@@ -121,7 +128,8 @@ class RolloutCollector:
         mom = torch.empty(D * (D + 1) // 2 + D, dtype=torch.float64, device=b.device)
         with torch.cuda.device(b.device):
             _lib.check(b.L.Cassie2dBatchBaselineMoments(b.h, self.task, self.obs.data_ptr(), returns.data_ptr(), self.done.data_ptr(),
-                                                        None, int(T), self._pidx.data_ptr(), mom.data_ptr(), _stream_ptr()), "BaselineMoments")
+                                                        self._path_start.data_ptr(), int(T), self._pidx.data_ptr(), mom.data_ptr(),
+                                                        _stream_ptr()), "BaselineMoments")
         m = mom.cpu().numpy()
         FtF = np.zeros((D, D)); iu = np.triu_indices(D)
         FtF[iu] = m[:D * (D + 1) // 2]; FtF = FtF + FtF.T - np.diag(np.diag(FtF))
@@ -159,7 +167,7 @@ class RolloutCollector:
                 sl = slice(start, k + 1)
                 out.append(dict(observations=obs[sl, e], actions=act[sl, e], rewards=rew[sl, e],
                                 agent_infos=dict(mean=mean[sl, e], log_std=np.tile(log_std, (k + 1 - start, 1))),
-                                env_infos={}, env=e, terminated=bool(done[k, e] == 1)))
+                                env_infos={}, env=e, start=start, terminated=bool(done[k, e] == 1)))
                 start = k + 1
         return out
 

@@ -76,7 +76,14 @@ enum { CASSIE_TASK_STAND = 0,    /* rllab/envs/cassie_stand2d.py:86-137: 17-d ob
 /* flags of Cassie2dBatchEnvStep */
 enum { CASSIE_AUTO_RESET = 1,        /* done envs are reset to the standing pose (cassie2d.py:78-88) */
        CASSIE_FRESH_OBS_ON_RESET = 2,/* fix SURVEY App. D.2: recompute the lagged op-space state on reset */
-       CASSIE_LIVE_QSTATE = 4 };     /* fix SURVEY App. D.4: imitation reward reads the live joint angles */
+       CASSIE_LIVE_QSTATE = 4,       /* fix SURVEY App. D.4: imitation reward reads the live joint angles */
+       CASSIE_TERMINAL_OBS = 8 };    /* with AUTO_RESET: return the terminal observation of a done env instead of
+                                        the observation env.reset() returns for its new episode (the default,
+                                        because the caller's next action must be computed from the new episode) */
+/* QP status in stats[.][3]: 0 optimal, 1 iteration cap, 2 factorisation failed, 3 = the env's state went
+ * non-finite (or beyond 1e10) and the env was reset: mj_checkPos / mj_checkVel / mj_checkAcc [EXT].  Such an env
+ * reports done = 1, reward 0 and the reset observation; its solver warm start and QP partition are cleared. */
+enum { CASSIE_STATUS_DIVERGED = 3 };
 
 /* Last error message of the calling thread ("" if none). */
 const char* CassieGetLastError(void);
@@ -182,6 +189,8 @@ int Cassie2dBatchSquatHost(CassieBatch* h, int mode, int n_steps, const void* ph
 /* solver statistics of the last Step/EnvStep/Squat call, DEVICE int32 [n][4]:
  * constraint rows, PGS sweeps, QP iterations, QP status of the last substep */
 int Cassie2dBatchGetStats(CassieBatch* h, int32_t* stats_dev, void* stream);
+/* policy steps since the last env reset of every env (the sampler's path position), DEVICE int32 [n] */
+int Cassie2dBatchGetEpisodeLengths(CassieBatch* h, int32_t* ep_len_dev, void* stream);
 /* solver warm start (mjData.qacc_warmstart, carried across steps and resets): DEVICE real [n][13].
  * Together with the general state this is the complete per-env simulator state. */
 int Cassie2dBatchSetWarmStart(CassieBatch* h, const void* qacc_dev, void* stream);

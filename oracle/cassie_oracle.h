@@ -156,6 +156,13 @@ void orc_cassie_osc_last(const orc_cassie* c, double x[39], double* obj, int* it
 long orc_rollout(const orc_model* phys, const orc_model* rbdl, int n_envs, int n_steps, int mode,
                  int hold, const double* actions, int adim, const double* phase,
                  const double* init_state26, double* out_state, int n_threads);
+/* persistent env pool (bench.py --impl reference): envs, QP hot start and squat clocks survive across calls */
+typedef struct orc_pool orc_pool;
+orc_pool* orc_pool_new(const orc_model* phys, const orc_model* rbdl, int n_envs);
+void orc_pool_free(orc_pool* p);
+long orc_pool_run(orc_pool* p, int n_steps, int mode, int hold, const double* actions, int adim,
+                  const double* phase, double* out_state, int n_threads);
+
 
 #ifdef __cplusplus
 }

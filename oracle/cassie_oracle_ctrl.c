@@ -590,3 +590,53 @@ long orc_rollout(const orc_model* phys, const orc_model* rbdl, int n_envs, int n
   }
   return total;
 }
+
+/* Persistent pool of facades for bench.py --impl reference: the envs (mjData, RBDL state, QP hot start,
+ * squat clock) stay alive from one bench "step" to the next, like the reference process that keeps its
+ * Cassie2d object for the whole squatting.py loop (squatting.py:6-16). */
+struct orc_pool { int n; orc_cassie** c; double* t; };
+orc_pool* orc_pool_new(const orc_model* phys, const orc_model* rbdl, int n_envs) {
+  orc_pool* p = (orc_pool*)calloc(1, sizeof(orc_pool));
+  p->n = n_envs;
+  p->c = (orc_cassie**)calloc((size_t)n_envs, sizeof(orc_cassie*));
+  p->t = (double*)calloc((size_t)n_envs, sizeof(double));
+  for (int e = 0; e < n_envs; e++) p->c[e] = orc_cassie_new(phys, rbdl);
+  return p;
+}
+void orc_pool_free(orc_pool* p) {
+  if (!p) return;
+  for (int e = 0; e < p->n; e++) orc_cassie_free(p->c[e]);
+  free(p->c); free(p->t); free(p);
+}
+/* n_steps more simulator steps of every env.  mode 0/1: actions [n_envs][nact][adim] held `hold` steps
+ * (indexed from step 0 of THIS call); mode 2/3: the squatting laws with per-env phase. */
+long orc_pool_run(orc_pool* p, int n_steps, int mode, int hold, const double* actions, int adim,
+                  const double* phase, double* out_state, int n_threads) {
+  long total = 0;
+  if (hold < 1) hold = 1;
+#ifdef _OPENMP
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total)
+  for (int e = 0; e < p->n; e++) {
+    orc_cassie* c = p->c[e];
+    const double w = 0.5 * 3.1415; /* squatting.py:8-9 */
+    double t = p->t[e];
+    int nact = (n_steps + hold - 1) / hold;
+    for (int k = 0; k < n_steps; k++) {
+      if (mode == 0) orc_cassie_step_torque(c, actions + ((size_t)e * nact + k / hold) * adim);
+      else if (mode == 1) orc_cassie_step_pd(c, actions + ((size_t)e * nact + k / hold) * adim);
+      else {
+        double ph = phase ? phase[e] : 0.0;
+        double zt = 0.7 + 0.25 * sin(w * t + ph), zdt = 0.25 * cos(w * t + ph);
+        if (mode == 2) { double f[6]; squat_jacobian_action(c, zt, zdt, f); orc_cassie_step_jacobian(c, f); }
+        else { double a[7]; squat_osc_action(c, zt, zdt, a); orc_cassie_step_osc(c, a); }
+        t = t + 0.0005;
+      }
+      total++;
+    }
+    p->t[e] = t;
+    if (out_state) orc_cassie_get_general_state(c, out_state + 26 * (size_t)e);
+  }
+  return total;
+}

@@ -64,6 +64,11 @@ def lib():
     L.orc_rollout.argtypes = [vp, vp, ct.c_int, ct.c_int, ct.c_int, ct.c_int, c_dp, ct.c_int,
                               c_dp, c_dp, c_dp, ct.c_int]
     L.orc_qp_solve.restype = ct.c_int
+    L.orc_pool_new.restype = vp
+    L.orc_pool_new.argtypes = [vp, vp, ct.c_int]
+    L.orc_pool_free.argtypes = [vp]
+    L.orc_pool_run.restype = ct.c_long
+    L.orc_pool_run.argtypes = [vp, ct.c_int, ct.c_int, ct.c_int, c_dp, ct.c_int, c_dp, c_dp, ct.c_int]
     L.orc_add_body.argtypes = [vp, ct.c_int, c_dp, c_dp, c_dp, ct.c_double, c_dp]
     L.orc_add_joint.argtypes = [vp, ct.c_int, ct.c_int, c_dp, c_dp, ct.c_double, ct.c_int, c_dp,
                                 ct.c_double, ct.c_double, c_dp, c_dp]
@@ -388,3 +393,25 @@ def rollout(model, n_envs, n_steps, mode, actions=None, hold=1, phase=None, init
                           None if a is None else _dp(a), adim, None if ph is None else _dp(ph),
                           None if i26 is None else _dp(i26), _dp(out), n_threads)
     return n, out
+
+
+class Pool:
+    """Persistent envs for bench.py --impl reference (facades, QP hot start and squat clocks survive across run() calls)."""
+
+    def __init__(self, model, n_envs):
+        self.m, self.n = model, n_envs
+        self.ptr = lib().orc_pool_new(model.ptr, model.rbdl_ptr, n_envs)
+
+    def run(self, n_steps, mode, actions=None, hold=1, phase=None, want_state=False, n_threads=0):
+        out = np.zeros((self.n, 26)) if want_state else None
+        adim = 0 if actions is None else actions.shape[-1]
+        a = None if actions is None else np.ascontiguousarray(actions, np.float64)
+        ph = None if phase is None else np.ascontiguousarray(phase, np.float64)
+        n = lib().orc_pool_run(self.ptr, n_steps, mode, hold, None if a is None else _dp(a), adim,
+                               None if ph is None else _dp(ph), None if out is None else _dp(out), n_threads)
+        return n, out
+
+    def close(self):
+        if self.ptr:
+            lib().orc_pool_free(self.ptr)
+            self.ptr = None

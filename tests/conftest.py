@@ -113,9 +113,18 @@ TORQUE_HIGH = np.array([12.0, 12.0, 0.9, 12.0, 12.0, 0.9])
 
 
 def rel_err(a, b):
-    """max |a-b| / max(1, |b|): the 'relative' error of the parity bar (qpos/qvel are O(1))."""
+    """max |a-b| / max(1, |b|): RELATIVE for |value| >= 1 and ABSOLUTE below 1 (most joint angles and
+    velocities of this robot are below 1, so for them the 1e-5 / 1e-9 bars of the parity tests are absolute
+    bounds in rad, m, rad/s, m/s).  DESIGN.md section 7 states this next to every tolerance."""
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
     return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))))
+
+
+def norm_rel_err(a, b):
+    """||a-b||_inf / ||b||_inf of one vector (qpos or qvel): the true norm-wise relative error."""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    d = float(np.max(np.abs(b)))
+    return float(np.max(np.abs(a - b))) / d if d > 0 else float(np.max(np.abs(a - b)))
 
 
 def squat_jacobian_action(s, t, phase=0.0):

@@ -68,9 +68,11 @@ def test_zero_substeps_and_masked_reset(E, LIB, oracle):
 
 def test_cold_path_fp32_single_step(E, LIB, oracle, omodel):
     """States with violated joint limits and tarsus / shin floor contacts (robots thrown around by
-    random torques): the out-of-line general constraint path in fp32, teacher-forced, 1e-5."""
+    random torques): the joint-limit / any-geom tiers of the constraint solver in fp32, one step from
+    identical fp32-representable states on both sides (test_gpu_fp32_bar.py protocol), 1e-5, masks bit-exact."""
     n = 24
     rng = np.random.default_rng(77)
+    f32 = lambda x: np.asarray(x, np.float64).astype(np.float32).astype(np.float64)
     pres = []; refs = []; acts = []; rmask = []; n_rare = 0
     for e in range(n):
         d = oracle.Data(omodel); d.set_state(QPOS_INIT_CTOR, np.zeros(13))
@@ -78,7 +80,9 @@ def test_cold_path_fp32_single_step(E, LIB, oracle, omodel):
         for k in range(500 + 10 * e):
             d.step(U[k // 10])
         (q, v), w = d.state(), d.warmstart()
-        a = U[(500 + 10 * e) // 10]
+        q, v, w = f32(q), f32(v), f32(w)
+        a = f32(U[(500 + 10 * e) // 10])
+        d.set_state(q, v); d.set_warmstart(w)
         d.step(a)
         ef = d.efc(); geoms = d.contacts()["geom"]           # geoms 5 / 9 are the toe capsules
         n_rare += bool((ef["type"] == 1).any() or any(g not in (5, 9) for g in geoms))
@@ -93,10 +97,8 @@ def test_cold_path_fp32_single_step(E, LIB, oracle, omodel):
     b.step_torque(torch.tensor(np.array(acts)), 1, contact_mask=mask)
     q, v = q_from_s26(b.get_general_state().cpu().numpy().astype(np.float64))
     err = np.abs(np.concatenate([q, v], axis=1) - np.array(refs)) / np.maximum(1, np.abs(np.array(refs)))
-    # lying robots carry up to ~40 rows with PGS far from converged: per-step error is larger than in the
-    # standing regime; stated tolerance 1e-4, masks bit-exact
-    assert err.max() < 1e-4, err.max()
-    assert np.median(err.max(axis=1)) < 1e-5
+    print("cold path fp32: worst %.2e, median of per-env worst %.2e" % (err.max(), np.median(err.max(axis=1))))
+    assert err.max() < 1e-5, err.max()
     assert np.array_equal(mask.cpu().numpy().astype(np.uint64), np.array(rmask, np.uint64))
     st = b.stats().cpu().numpy()
     assert (st[:, 0] >= 4).all() and (st[:, 1] <= 50).all()
@@ -125,7 +127,9 @@ def test_error_reporting(E, LIB):
 
 def test_imitation_env_live_qstate(E, LIB, oracle, omodel):
     """cassie2d.py reward with the fix of SURVEY App. D.4 (reference_faithful=False): qstate follows the
-    robot, so episodes no longer end at their first step; checked against the Python formula."""
+    robot, so episodes no longer end at their first step; checked against the Python formula at EVERY policy
+    step, teacher-forced (the PD-held robot amplifies rounding chaotically, DESIGN section 7, so each policy step
+    starts from the oracle's state on both sides)."""
     from cassierl_b200.trajectory import Cassie2dTraj
     tr = Cassie2dTraj()
     n, T = 4, 8
@@ -138,6 +142,10 @@ def test_imitation_env_live_qstate(E, LIB, oracle, omodel):
     rng = np.random.default_rng(5)
     t = 0.0
     for k in range(T):
+        if k > 0:
+            S = np.array([s26(oracle, *c.data.state()) for c in refs]); Wm = np.array([c.data.warmstart() for c in refs])
+            env.batch.reset(torch.tensor(S, dtype=torch.float64, device=env.batch.device))
+            env.batch.set_warm_start(torch.tensor(Wm))
         A = tr.qpos[min(10 * (k + 1), 1681)][[3, 4, 6, 8, 9, 11]] + 0.02 * rng.standard_normal((n, 6))
         obs, rew, done = env.step(torch.tensor(A), n=10)
         obs, rew = obs.cpu().numpy(), rew.cpu().numpy()
@@ -145,15 +153,84 @@ def test_imitation_env_live_qstate(E, LIB, oracle, omodel):
             t += 0.0005
         ref = tr.state(t)[0][[0, 1, 2, 3, 4, 6, 8, 9, 11]]
         for e, c in enumerate(refs):
-            if k > 0:
-                continue_state = None
             for _ in range(10):
                 c.step_pd(A[e])
             s = c.op_state(); q, _ = c.data.state()
             j = q[[3, 4, 6, 8, 9, 11]].sum() - ref[3:].sum()
             p = s[0] + s[1] - ref[0] - ref[1]; o = s[2] - ref[2]
             r = 0.5 * np.exp(-j * j) + 0.3 * np.exp(-p * p) + 0.1 * np.exp(-o * o)
-            if k == 0:   # later steps diverge chaotically under PD; the formula is what is tested
-                assert abs(rew[e] - r) < 1e-8, (k, e)
-                assert np.array_equal(obs[e, 17:], ref)
+            assert abs(rew[e] - r) < 1e-8, (k, e)
+            assert np.array_equal(obs[e, 17:], ref), (k, e)
+    env.terminate()
+
+
+def test_auto_reset_returns_reset_observation(E, LIB, oracle):
+    """with CASSIE_AUTO_RESET the observation of a done env is the one env.reset() returns (the caller's
+    next action belongs to the new episode); CASSIE_TERMINAL_OBS keeps the terminal observation."""
+    n = 64
+    rng = np.random.default_rng(9)
+    envs = {k: E.Cassie2dBatchEnv(n, task="stand", control_mode="Torque", precision=64, auto_reset=True, terminal_obs=k)
+            for k in (False, True)}
+    for env in envs.values():
+        env.reset()
+    seen = 0
+    for k in range(80):
+        a = torch.tensor(rng.uniform(-1, 1, (n, 6)) * TORQUE_HIGH)
+        o0, r0, d0 = [x.clone() for x in envs[False].step(a)]
+        o1, r1, d1 = [x.clone() for x in envs[True].step(a)]
+        assert torch.equal(d0, d1) and torch.equal(r0, r1)
+        dm = d0.bool()
+        assert torch.equal(o0[~dm], o1[~dm])
+        if dm.any():
+            seen += int(dm.sum())
+            assert (o1[dm][:, 0] < 0.5).all()                    # terminal observation: the fallen robot (z < 0.5)
+            # reset observation: stale lagged op-space state (App. D.2) but the FRESH pitch / pitch rate of the reset pose
+            assert (o0[dm][:, 1] == 0).all() and (o0[dm][:, 4] == 0).all()
+            s = envs[False].batch.get_general_state()
+            assert torch.allclose(s[dm][:, 1], torch.tensor(0.939, dtype=s.dtype, device=s.device))
+            # the same thing EnvReset would now return for these envs: obs built from the stored op-space state
+            o18 = envs[False].batch.get_operational_space_state()[dm]
+            want = o18[:, 1:18].clone(); want[:, 5] -= o18[:, 0]; want[:, 11] -= o18[:, 0]
+            assert torch.equal(o0[dm], want)
+    assert seen > 0
+    for env in envs.values():
+        env.terminate()
+
+
+def test_non_finite_env_is_reset_and_flagged(E, LIB, oracle):
+    """a NaN / Inf env reports done, reward 0, a finite observation, is reset (solver state too) and
+    flagged with status 3 in the stats; its neighbours are untouched (mj_checkPos/Vel/Acc [EXT])."""
+    n = 32
+    ref = E.Cassie2dBatchEnv(n, task="stand", control_mode="PD", precision=32, auto_reset=False)
+    env = E.Cassie2dBatchEnv(n, task="stand", control_mode="PD", precision=32, auto_reset=False)
+    ref.reset(); env.reset()
+    a = torch.tensor(np.tile(QPOS_INIT_PY[[3, 4, 6, 8, 9, 11]], (n, 1)))
+    s = env.batch.get_general_state().clone()
+    s[5, 7] = float("nan"); s[9, 1] = float("inf"); s[20, 3] = 1e12
+    env.batch.reset(s)
+    o, r, d = [x.clone() for x in env.step(a)]
+    o2, r2, d2 = [x.clone() for x in ref.step(a)]
+    bad = torch.zeros(n, dtype=torch.bool, device=o.device); bad[[5, 9, 20]] = True
+    assert torch.isfinite(o).all() and torch.isfinite(r).all()
+    assert (d[bad] == 1).all() and (r[bad] == 0).all()
+    assert torch.equal(o[~bad], o2[~bad]) and torch.equal(r[~bad], r2[~bad]) and torch.equal(d[~bad], d2[~bad])
+    st = env.batch.stats()
+    assert (st[bad][:, 3] == LIB.STATUS_DIVERGED).all() and (st[~bad][:, 3] != LIB.STATUS_DIVERGED).all()
+    g = env.batch.get_general_state()
+    assert torch.isfinite(g).all() and torch.allclose(g[bad][:, 1], torch.tensor(0.939, device=g.device))
+    assert (env.batch.get_warm_start()[bad] == 0).all()
+    # and the env lives on
+    o, r, d = env.step(a)
+    assert torch.isfinite(o).all() and torch.isfinite(r).all()
+    env.terminate(); ref.terminate()
+
+
+def test_imitation_reset_observation_has_zero_reference_slots(E, LIB):
+    """env.reset() of cassie2d.py returns zeros in obs[17:26] (cassie2d.py:78-95); step() fills them."""
+    env = E.Cassie2dBatchEnv(4, task="imitate", control_mode="PD", precision=64, auto_reset=False)
+    o = env.reset().clone()
+    assert (o[:, 17:] == 0).all() and (o[:, 0] > 0.9).all()
+    a = torch.tensor(np.tile(QPOS_INIT_PY[[3, 4, 6, 8, 9, 11]], (4, 1)))
+    o, _, _ = env.step(a)
+    assert (o[:, 17:] != 0).any()
     env.terminate()

@@ -279,11 +279,14 @@ def test_env_step_stand_fp64(E, LIB, oracle, omodel, mode):
         obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
         for e, c in enumerate(refs):
             sp, r, d = py_stand_step(oracle, c, A[k, e], mode)
-            assert rel_err(obs[e], sp) < 1e-8, (k, e)
             assert abs(rew[e] - r) < 1e-8 * max(1, abs(r)), (k, e)
             assert bool(done[e]) == d, (k, e)
             if d:
+                # auto-reset convention (include/cassie2d.h): a done env returns the observation env.reset() gives
+                # (cassie_stand2d.py:75-84: stale lagged op-space state, fresh pitch), not its terminal observation
                 c.reset(st); n_done += 1
+                s = c.op_state(); sp = s[1:18].copy(); sp[5] -= s[0]; sp[11] -= s[0]
+            assert rel_err(obs[e], sp) < 1e-8, (k, e)
         # auto-reset: done envs are back at the reset pose on device, the others carry on
         q, v = q_from_s26(env.batch.get_general_state().cpu().numpy())
         for e, c in enumerate(refs):

@@ -122,7 +122,8 @@ def test_discounted_returns(R):
     for p in col.paths(pol, envs=[0, 1]):
         r = p["rewards"].astype(np.float64)
         dc = np.array([np.sum(r[i:] * 0.99 ** np.arange(len(r) - i)) for i in range(len(r))])
-        e = p["env"]
+        e, a = p["env"], p["start"]
+        assert np.allclose(ret[a:a + len(r), e], dc, rtol=1e-5, atol=1e-5), (e, a)
     col.close()
 
 

@@ -38,7 +38,8 @@ def _worker(rank, world, port, n_total, q):
         g = torch.Generator().manual_seed(7)
         T = 5
         rew_all = torch.rand(T, n_total, generator=g, dtype=torch.float64)
-        done_all = (torch.rand(T, n_total, generator=g) < 0.2)
+        # the rollout kernel's flag: 0 running, 1 env terminated, 2 max_path_length reached
+        done_all = torch.randint(0, 3, (T, n_total), generator=g, dtype=torch.uint8) * (torch.rand(T, n_total, generator=g) < 0.3).to(torch.uint8)
         obs_all = torch.rand(T, n_total, 17, generator=g)
         st = P.RolloutStats()
         for t in range(T):
@@ -46,7 +47,8 @@ def _worker(rank, world, port, n_total, q):
         red = st.reduce()
         gathered = P.gather_paths(obs_all[:, ids].contiguous(), n_total)
         ok = (abs(red["reward_sum"] - float(rew_all.sum())) < 1e-9 and red["steps"] == T * n_total
-              and red["episodes"] == float(done_all.sum()) and torch.equal(gathered, obs_all))
+              and red["episodes"] == float((done_all != 0).sum()) and red["truncated"] == float((done_all == 2).sum())
+              and red["terminated"] + red["truncated"] == red["episodes"] and torch.equal(gathered, obs_all))
         q.put((rank, bool(ok), red["mean_reward"]))
     finally:
         dist.destroy_process_group()
