@@ -432,9 +432,15 @@ def run_native(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        traffic = None                                         # DRAM bytes per launch from the last ncu --set full capture
+        # DRAM bytes per launch from the last `ncu --set full` capture of this workload -- printed only while the
+        # capture's kernel sources are the ones being timed (profiles/traffic.json records their hash), else null
+        traffic, traffic_src = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl, {}).get("dram_bytes_per_launch")
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl, {})
+            if tr.get("kernel_source_sha16") == kernel_source_hash():
+                traffic, traffic_src = tr.get("dram_bytes_per_launch"), tr.get("capture")
+            elif tr:
+                traffic_src = "stale: capture %s ran other kernel sources" % tr.get("capture")
         except Exception:
             pass
         fp32_peak = L.CassieMeasureFp32Peak(local)            # TFLOP/s, measured live on this GPU

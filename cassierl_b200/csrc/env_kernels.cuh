@@ -413,8 +413,9 @@ __global__ void __launch_bounds__(128) k_get_op(const BatchView<T> v, T* __restr
 // ---------------------------------------------------------------------------------------
 inline unsigned grid_for(int n, int block) { return (unsigned)((n + block - 1) / block); }
 
+// thread-per-env launchers (launch.cuh picks between these and the quad engine's, quad_kernels.cuh)
 template <typename T>
-cudaError_t Launch<T>::step(const ModelPair<T>& mp, const BatchView<T>& v, const StepArgs& a, cudaStream_t s) {
+cudaError_t thread_step(const ModelPair<T>& mp, const BatchView<T>& v, const StepArgs& a, cudaStream_t s) {
   const T* act = (const T*)a.action;
   const int bt = block_threads(a.mode);
   const unsigned g = grid_for(v.n, bt);
@@ -430,7 +431,7 @@ cudaError_t Launch<T>::step(const ModelPair<T>& mp, const BatchView<T>& v, const
 }
 
 template <typename T>
-cudaError_t Launch<T>::env_step(const ModelPair<T>& mp, const BatchView<T>& v, const EnvStepArgs& a, cudaStream_t s) {
+EnvStepDev<T> make_env_step_dev(const EnvStepArgs& a) {
   EnvStepDev<T> d;
   d.task = a.task; d.flags = a.flags; d.n_sub = a.n_substeps;
   d.action = (const T*)a.action; d.obs = (T*)a.obs; d.reward = (T*)a.reward; d.done = a.done;
@@ -439,6 +440,11 @@ cudaError_t Launch<T>::env_step(const ModelPair<T>& mp, const BatchView<T>& v, c
                          0.0, 0.0, 0.0, 0.0, 0.0, 0.68111815, -1.40730357, 1.62972042, -1.77611107, -0.61968407,
                          0.0, 0.0, 0.0, 0.0, 0.0};
   for (int i = 0; i < 26; i++) d.reset_state[i] = (T)qi[i];
+  return d;
+}
+template <typename T>
+cudaError_t thread_env_step(const ModelPair<T>& mp, const BatchView<T>& v, const EnvStepArgs& a, cudaStream_t s) {
+  const EnvStepDev<T> d = make_env_step_dev<T>(a);
   const int bt = block_threads(a.mode);
   const unsigned g = grid_for(v.n, bt);
   switch (a.mode) {
@@ -452,7 +458,7 @@ cudaError_t Launch<T>::env_step(const ModelPair<T>& mp, const BatchView<T>& v, c
 }
 
 template <typename T>
-cudaError_t Launch<T>::squat(const ModelPair<T>& mp, const BatchView<T>& v, const SquatArgs& a, cudaStream_t s) {
+cudaError_t thread_squat(const ModelPair<T>& mp, const BatchView<T>& v, const SquatArgs& a, cudaStream_t s) {
   const int bt = block_threads(a.mode);
   const unsigned g = grid_for(v.n, bt);
   if (a.mode == kModeJacobian) k_squat<T, kModeJacobian><<<g, bt, 0, s>>>(mp, v, (const T*)a.phase, a.n_steps, a.contact_mask);

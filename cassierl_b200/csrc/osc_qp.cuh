@@ -42,16 +42,12 @@ constexpr int kQpGreedyIters = 60;
 constexpr int kOscWsDoubles = (kQpTasks + 1) * kQpN + 2 * kQpTri;   // E, G, L
 
 // G and the Cholesky factor are packed lower triangles (105 entries): half the thread-local lines.
-CASSIE_HD void box_qp_solve(const double G[kQpTri], const double g[kQpN], const double lo[kQpN],
-                            const double hi[kQpN], double z[kQpN], unsigned& at_lo, unsigned& at_hi, int max_iter,
-                            OscStats* st, double* Lws = nullptr) {
+// GA / VA / LA: anything indexable with [] that yields double (plain pointers in the thread-per-env engine, strided
+// shared-memory views in the quad engine, quad_rt.cuh SV<double>)
+template <typename GA, typename VA, typename ZA, typename LA>
+CASSIE_HD void box_qp_solve_on(const GA G, const VA g, const VA lo, const VA hi, ZA z, LA L, unsigned& at_lo, unsigned& at_hi,
+                               int max_iter, OscStats* st) {
   double grad[kQpN], invd[kQpN];  // invd = 1 / L_ii: one division per pivot instead of one per entry
-#if defined(__CUDA_ARCH__) && !defined(CASSIE_NO_OSC_OVERLAY)
-  double* const L = Lws;
-#else
-  double Lloc[kQpTri];
-  double* const L = Lws ? Lws : Lloc;
-#endif
   double gscale = 1.0;
   for (int i = 0; i < kQpN; i++) gscale = fmax(gscale, fabs(g[i]));
   const double dtol = 1e-12 * gscale;
@@ -148,6 +144,16 @@ CASSIE_HD void box_qp_solve(const double G[kQpTri], const double g[kQpN], const 
   }
   for (int i = 0; i < kQpN; i++) z[i] = z[i] < lo[i] ? lo[i] : (z[i] > hi[i] ? hi[i] : z[i]);
   if (st) { st->iters = it; st->status = status; }
+}
+CASSIE_HD void box_qp_solve(const double G[kQpTri], const double g[kQpN], const double lo[kQpN],
+                            const double hi[kQpN], double z[kQpN], unsigned& at_lo, unsigned& at_hi, int max_iter,
+                            OscStats* st, double* Lws = nullptr) {
+#if defined(__CUDA_ARCH__) && !defined(CASSIE_NO_OSC_OVERLAY)
+  box_qp_solve_on(G, g, lo, hi, z, Lws, at_lo, at_hi, max_iter, st);
+#else
+  double Lloc[kQpTri];
+  box_qp_solve_on(G, g, lo, hi, z, Lws ? Lws : Lloc, at_lo, at_hi, max_iter, st);
+#endif
 }
 
 // OSC_RBDL::RunPTSC for the planar model.  act = ControllerOsc in memory order (RobotInterface.h:23-28):

@@ -1,0 +1,16 @@
+#!/bin/bash
+set -u
+TAG=${1:-r2d}
+mkdir -p gpurun_out
+echo "== pytest -m gpu (quad engine)"; timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 | tee gpurun_out/${TAG}_pytest.txt
+for pre in 100 1000; do
+for wl in squat_osc squat_jacobian pd_env; do
+  echo "== bench quad $wl pre=$pre"; timeout 300 python bench.py --workload $wl --steps 20 --warmup 3 --preadvance $pre --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/${TAG}_bench_${wl}_${pre}.json | python -c "
+import sys,json
+try:
+    d=json.loads(sys.stdin.read()); print('   value %.4g  e2e %.4g  frac %.4f  ms %.4f  rows %.2f->%.2f max %d' % (d['value'], d['e2e']['value'], d['roofline']['frac'], d['ms_per_step'], d['stats']['first_timed_step']['rows_mean'], d['stats']['last_step']['rows_mean'], d['stats']['last_step']['rows_max']))
+except Exception as e: print('   parse failed', e)
+"
+done
+done
+bash tools/gpu_prof2.sh ${TAG} squat_osc:k_qsquat:100 | grep -v "^{" | head -60
