@@ -29,11 +29,12 @@ struct CtrlLayout {
   static constexpr int e0 = task + 64;               // Jdot qd - xdd* per task row [12]
   static constexpr int r0 = e0 + 12;                 // task residual at z = 0 [12]
   static constexpr int E = r0 + 12;                  // [12][14]
-  static constexpr int end = E + 12 * kQpN;
+  static constexpr int end = E + kQpTri + 3 + 5 * kQpN > E + 12 * kQpN ? E + kQpTri + 3 + 5 * kQpN : E + 12 * kQpN;
   // QP overlay: everything below `e0` is dead once the task loop is over
-  static constexpr int G = 0, g = G + kQpTri, Lw = g + kQpN, lo = Lw + kQpTri, hi = lo + kQpN, z = hi + kQpN;
-  static_assert(lo <= e0, "G, g and L must not touch e0 / r0 / E while G is being built");
-  static_assert(z + kQpN <= end, "QP vectors (written after G is complete) stay inside the block");
+  // QP overlay: G (full symmetric 14 x 14) and g are written while E / r0 are read; the factor and the QP's vectors
+  // reuse E once G is complete
+  static constexpr int G = 0, g = G + kQpN * kQpN, Lw = E, qpv = Lw + kQpTri + 3;
+  static_assert(g + kQpN <= e0, "G and g must not touch e0 / r0 / E while G is being built");
   // Jacobian mode: B = Nc Bt (13 x 6) and the right-hand side, gathered for lane 0
   static constexpr int jacB = E, jacRhs = jacB + kNV * kNU;
 };
@@ -253,183 +254,245 @@ QUAD_FN void quad_project(const Lane ln, SV<TC> C, const QuadCtrlDyn& d, V8<TC> 
 
 // ---------------------------------------------------------------------------------------------------------------
 // The 14-variable box QP of osc_qp.cuh (block principal pivoting, same exchange rule, same tolerances) on four lanes.
-// Lane l owns rows l, l + 4, l + 8, (l + 12) of the KKT matrix of the current partition: G with the pinned variables
-// replaced by identity rows / columns.  The Cholesky factor lives in registers (row slot s of lane l = row 4 s + l,
-// 4 s + 4 entries allocated); a pivot and the scaled column below it reach the other lanes by shuffles, the trailing
-// update is local.  Forward substitution is column oriented (one broadcast per unknown), backward substitution sums
-// the lanes' partial dot products.  All partition logic runs replicated on the four lanes (same data, same decisions).
-QUAD_FN void quad_box_qp(const Lane ln, SV<TC> G, SV<TC> g, const PlanarModel<TC>& m, TC z[kQpN], unsigned& at_lo, unsigned& at_hi,
-                         int max_iter, OscStats* st) {
+// Every pass solves the KKT system of the current partition on the masked matrix (pinned variables become identity
+// rows / columns).  Lane l owns rows l, l + 4, l + 8, l + 12 ("row slots" s = 0..3) of the matrix and of every vector
+// and keeps them IN REGISTERS for the whole factorisation; a pivot column reaches the other lanes through a small
+// double-buffered shared-memory column (one barrier per pivot: the owners publish the unscaled column, everybody
+// reads pivot + column in one batch, scales locally and updates its rows), forward substitution broadcasts one
+// unknown per step by shuffle, backward substitution sums the lanes' partial dots by shuffles.  Every loop is
+// unrolled through template recursion over the pivot (a `#pragma unroll` nest of this size is silently left rolled
+// by the compiler, and the row arrays then live in local memory: profiles/r2f_squat_osc.txt, 25 % of the kernel's
+// stall samples; rolled shared-memory loops spent 37 % of the instructions on index arithmetic and, unrolled,
+// serialised on the store -> load order of the shared array: r2g, r2i).  The partition logic runs replicated.
+//   G: full symmetric 14 x 14, g: gradient (read only)    V: 5 x 14 doubles of vector scratch
+struct QpRegs {
+  TC L0[4], L1[8], L2[12], L3[14];   // row slot s holds row 4 s + l, entries 0 .. 4 s + 3 (those right of the diagonal unused)
+  TC rhs[4];                         // right-hand side / solution entries of the own rows
+  TC invd[kQpN];                     // 1 / L_jj, replicated
+  TC z[kQpN];                        // solution, replicated
+};
+template <int S> QUAD_FN TC& qp_row(QpRegs& R, int k) {
+  if (S == 0) return R.L0[k < 4 ? k : 3];
+  if (S == 1) return R.L1[k < 8 ? k : 7];
+  if (S == 2) return R.L2[k < 12 ? k : 11];
+  return R.L3[k < 14 ? k : 13];
+}
+template <int J, int S>
+QUAD_FN void qp_pivot_slot(QpRegs& R, const TC (&ck)[kQpN], TC inv) {
+  if (4 * S + 3 >= J) {
+    const TC lij = qp_row<S>(R, J) * inv;   // row = pivot row: becomes sqrt(d); rows above the pivot: unused word
+    qp_row<S>(R, J) = lij;
+    CASSIE_UNROLL
+    for (int k = J + 1; k <= 4 * S + 3 && k < kQpN; k++) qp_row<S>(R, k) -= lij * ck[k];
+  }
+}
+template <int J>
+struct QpPivot {
+  static QUAD_FN void run(QpRegs& R, const Lane ln, SV<TC> col, bool& ok) {
+    const int l = ln.ql;
+    const SV<TC> buf = col.at((J & 1) * kQpN);
+    // owners publish the unscaled column J (rows >= J)
+    if (4 * 0 + 3 >= J) { if (4 * 0 + l >= J) buf[4 * 0 + l] = qp_row<0>(R, J); }
+    if (4 * 1 + 3 >= J) { if (4 * 1 + l >= J) buf[4 * 1 + l] = qp_row<1>(R, J); }
+    if (4 * 2 + 3 >= J) { if (4 * 2 + l >= J) buf[4 * 2 + l] = qp_row<2>(R, J); }
+    if (4 * 3 + l >= J && 4 * 3 + l < kQpN) buf[4 * 3 + l] = qp_row<3>(R, J);
+    wsync();
+    TC djj = buf[J];
+    TC ck[kQpN];
+    CASSIE_UNROLL
+    for (int k = J + 1; k < kQpN; k++) ck[k] = buf[k];
+    if (!(djj > 0.0)) { ok = false; djj = 1.0; }
+#ifdef __CUDA_ARCH__
+    const TC inv = rsqrt(djj);
+#else
+    const TC inv = 1.0 / sqrt(djj);
+#endif
+    R.invd[J] = inv;
+    CASSIE_UNROLL
+    for (int k = J + 1; k < kQpN; k++) ck[k] *= inv;
+    qp_pivot_slot<J, 0>(R, ck, inv);
+    qp_pivot_slot<J, 1>(R, ck, inv);
+    qp_pivot_slot<J, 2>(R, ck, inv);
+    qp_pivot_slot<J, 3>(R, ck, inv);
+    QpPivot<J + 1>::run(R, ln, col, ok);
+  }
+};
+template <>
+struct QpPivot<kQpN> {
+  static QUAD_FN void run(QpRegs&, const Lane, SV<TC>, bool&) {}
+};
+// forward substitution L y = rhs, one unknown per step, broadcast by shuffle
+template <int K>
+struct QpForward {
+  static QUAD_FN void run(QpRegs& R, const Lane ln) {
+    const int l = ln.ql;
+    const TC yk = shfl(R.rhs[K / 4] * R.invd[K], K % 4);
+    R.rhs[K / 4] = (K % 4 == l) ? yk : R.rhs[K / 4];
+    if (4 * 0 + 3 > K) R.rhs[0] -= (4 * 0 + l > K) ? qp_row<0>(R, K) * yk : TC(0);
+    if (4 * 1 + 3 > K) R.rhs[1] -= (4 * 1 + l > K) ? qp_row<1>(R, K) * yk : TC(0);
+    if (4 * 2 + 3 > K) R.rhs[2] -= (4 * 2 + l > K) ? qp_row<2>(R, K) * yk : TC(0);
+    R.rhs[3] -= (4 * 3 + l > K && 4 * 3 + l < kQpN) ? qp_row<3>(R, K) * yk : TC(0);
+    QpForward<K + 1>::run(R, ln);
+  }
+};
+template <>
+struct QpForward<kQpN> {
+  static QUAD_FN void run(QpRegs&, const Lane) {}
+};
+// backward substitution L' z = y: z_a = (y_a - sum_{k > a} L_ka z_k) / L_aa, the sum spread over the row owners
+template <int A>
+struct QpBackward {
+  static QUAD_FN void run(QpRegs& R, const Lane ln) {
+    const int l = ln.ql;
+    TC part = TC(0);
+    if (4 * 0 + 3 > A) part += (4 * 0 + l > A) ? qp_row<0>(R, A) * R.rhs[0] : TC(0);
+    if (4 * 1 + 3 > A) part += (4 * 1 + l > A) ? qp_row<1>(R, A) * R.rhs[1] : TC(0);
+    if (4 * 2 + 3 > A) part += (4 * 2 + l > A) ? qp_row<2>(R, A) * R.rhs[2] : TC(0);
+    part += (4 * 3 + l > A && 4 * 3 + l < kQpN) ? qp_row<3>(R, A) * R.rhs[3] : TC(0);
+    part += shx(part, 1);
+    part += shx(part, 2);
+    const TC za = shfl((R.rhs[A / 4] - part) * R.invd[A], A % 4);
+    R.rhs[A / 4] = (A % 4 == l) ? za : R.rhs[A / 4];
+    R.z[A] = za;
+    QpBackward<A - 1>::run(R, ln);
+  }
+};
+template <>
+struct QpBackward<-1> {
+  static QUAD_FN void run(QpRegs&, const Lane) {}
+};
+
+QUAD_FN void quad_box_qp(const Lane ln, SV<TC> G, SV<TC> g, SV<TC> V, const PlanarModel<TC>& m, TC z[kNU],
+                         unsigned& at_lo, unsigned& at_hi, int max_iter, OscStats* st) {
+  constexpr int N = kQpN;
   const int l = ln.ql;
-  TC lo[kQpN], hi[kQpN], gv[kQpN];
+  const SV<TC> zb = V, col = V.at(N), mult = V.at(3 * N), zfin = V.at(4 * N);
+  SV<TC> Grow[4];
   CASSIE_UNROLL
-  for (int i = 0; i < kQpN; i++) {
-    lo[i] = i < kNU ? m.act_lo[i < kNU ? i : 0] : TC(0);
-    hi[i] = i < kNU ? m.act_hi[i < kNU ? i : 0] : TC(1e30);
-    gv[i] = g[i];
+  for (int s = 0; s < 4; s++) {
+    const int i = 4 * s + l;
+    Grow[s] = G.at((i < N ? i : N - 1) * N);
+  }
+  const bool has3 = l < 2;
+  TC lo_own[4], hi_own[4], g_own[4];
+  CASSIE_UNROLL
+  for (int s = 0; s < 4; s++) {
+    const int i = 4 * s + l;
+    lo_own[s] = i < kNU ? m.act_lo[i < kNU ? i : 0] : TC(0);
+    hi_own[s] = i < kNU ? m.act_hi[i < kNU ? i : 0] : TC(1e30);
+    g_own[s] = g[i < N ? i : N - 1];
   }
   TC gscale = 1.0;
   CASSIE_UNROLL
-  for (int i = 0; i < kQpN; i++) gscale = fmax(gscale, fabs(gv[i]));
+  for (int i = 0; i < N; i++) gscale = fmax(gscale, fabs(g[i]));
   const TC dtol = 1e-12 * gscale;
-  int it = 0, status = 1, best = kQpN + 1;
-  // The loop is WARP UNIFORM (the shuffles below name all 32 lanes): a quad whose QP is finished keeps iterating on its
-  // frozen partition until the slowest quad of the warp is done; its outputs are latched in zf / status / it.
+  int it = 0, status = 1, best = N + 1;
+  // The loop is WARP UNIFORM (its collectives name all 32 lanes): a quad whose QP is finished keeps iterating on its
+  // frozen partition until the slowest quad of the warp is done; its outputs are latched in zfin / status / it.
   bool fin = false;
-  TC zf[kQpN];
-  CASSIE_UNROLL
-  for (int i = 0; i < kQpN; i++) zf[i] = TC(0);
   CASSIE_ROLL
   for (int pass = 0; pass < max_iter; pass++) {
     const unsigned fixed = at_lo | at_hi;
-    TC zb[kQpN];   // pinned values (0 for free variables)
-    CASSIE_UNROLL
-    for (int i = 0; i < kQpN; i++) zb[i] = ((at_lo >> i) & 1u) ? lo[i] : (((at_hi >> i) & 1u) ? hi[i] : TC(0));
-    // own rows of the masked KKT matrix and right-hand side
-    TC Lr0[4], Lr1[8], Lr2[12], Lr3[16], rhs[4];
-    CASSIE_UNROLL
-    for (int s = 0; s < 4; s++) {
-      const int i = 4 * s + l;               // row of this slot (i >= 14 on the unused slot 3 of lanes 2, 3)
-      const bool valid = i < kQpN;
-      const bool pin = valid ? ((fixed >> i) & 1u) != 0u : true;
-      TC acc = TC(0);
-      CASSIE_UNROLL
-      for (int j = 0; j < 4 * s + 4; j++) {
-        if (j < kQpN) {
-          // G[qtri(i, j)] for every j of the row: entries right of the diagonal come from the symmetric partner
-          const TC gij = valid ? G[qtri(i, j)] : TC(0);
-          acc += gij * zb[j];
-          const bool pj = ((fixed >> j) & 1u) != 0u;
-          const TC kij = (pin || pj) ? ((i == j) ? TC(1) : TC(0)) : gij;
-          if (s == 0) Lr0[j] = kij; else if (s == 1) Lr1[j] = kij; else if (s == 2) Lr2[j] = kij; else Lr3[j] = kij;
-        }
-      }
-      // columns right of the allocated part of the row (j >= 4 s + 4) still enter rhs_i = -(g_i + sum_j G_ij zB_j)
-      CASSIE_UNROLL
-      for (int j = 4 * s + 4; j < kQpN; j++) acc += (valid ? G[qtri(i, j)] : TC(0)) * zb[j];
-      TC gi = TC(0), zi = TC(0);
-      CASSIE_UNROLL
-      for (int j = 0; j < kQpN; j++) { gi = (j == i) ? gv[j] : gi; zi = (j == i) ? zb[j] : zi; }
-      rhs[s] = pin ? zi : -(gi + acc);
-    }
-    // ---- right-looking Cholesky, pivots broadcast
-    bool ok = true;
-    TC invd[kQpN];
-#define QP_L(s, j) ((s) == 0 ? Lr0[(j) < 4 ? (j) : 0] : (s) == 1 ? Lr1[(j) < 8 ? (j) : 0] : (s) == 2 ? Lr2[(j) < 12 ? (j) : 0] : Lr3[(j) < 16 ? (j) : 0])
-    CASSIE_UNROLL
-    for (int j = 0; j < kQpN; j++) {
-      TC djj = shfl(QP_L(j / 4, j), j % 4);
-      if (!(djj > 0.0)) { ok = false; djj = 1.0; }
-#ifdef __CUDA_ARCH__
-      const TC inv = rsqrt(djj);
-#else
-      const TC inv = 1.0 / sqrt(djj);
-#endif
-      invd[j] = inv;
-      // scale column j in every own row (the pivot row itself becomes sqrt(d))
-      if (j < 4) Lr0[j] *= inv;
-      if (j < 8) Lr1[j] *= inv;
-      if (j < 12) Lr2[j] *= inv;
-      Lr3[j] *= inv;
-      CASSIE_UNROLL
-      for (int k = j + 1; k < kQpN; k++) {
-        const TC ckj = shfl(QP_L(k / 4, j), k % 4);
-        if (k < 4) Lr0[k] -= Lr0[j] * ckj;
-        if (k < 8 && j < 8) Lr1[k] -= Lr1[j] * ckj;
-        if (k < 12 && j < 12) Lr2[k] -= Lr2[j] * ckj;
-        Lr3[k] -= Lr3[j] * ckj;
-      }
-    }
-    // ---- forward substitution L y = rhs (column oriented)
-    CASSIE_UNROLL
-    for (int k = 0; k < kQpN; k++) {
-      const TC yk = shfl(rhs[k / 4], k % 4) * invd[k];
-      // owner keeps y_k in place of its rhs
-      if (k % 4 == l) rhs[k / 4] = yk;
-      if (k < 4) { if (4 * 0 + l > k) rhs[0] -= Lr0[k] * yk; }
-      if (k < 8) { if (4 * 1 + l > k) rhs[1] -= Lr1[k] * yk; }
-      if (k < 12) { if (4 * 2 + l > k) rhs[2] -= Lr2[k] * yk; }
-      if (4 * 3 + l > k) rhs[3] -= Lr3[k] * yk;
-    }
-    // ---- backward substitution L' z = y: z_a = (y_a - sum_{k > a} L_ka z_k) / L_aa, the sum spread over the row owners
-    CASSIE_UNROLL
-    for (int a = kQpN - 1; a >= 0; a--) {
-      TC part = TC(0);
-      if (a < 4) { if (4 * 0 + l > a) part += Lr0[a] * rhs[0]; }
-      if (a < 8) { if (4 * 1 + l > a) part += Lr1[a] * rhs[1]; }
-      if (a < 12) { if (4 * 2 + l > a && 4 * 2 + l < kQpN) part += Lr2[a] * rhs[2]; }
-      if (4 * 3 + l > a && 4 * 3 + l < kQpN) part += Lr3[a] * rhs[3];
-      part += shx(part, 1);
-      part += shx(part, 2);
-      const TC ya = shfl(rhs[a / 4], a % 4);
-      const TC za = (ya - part) * invd[a];
-      if (a % 4 == l) rhs[a / 4] = za;
-      z[a] = za;
-    }
-#undef QP_L
-    // ---- violations: free variables outside their bounds, pinned variables with a wrong-sign multiplier (osc_qp.cuh)
-    TC zmax = 1.0;
-    CASSIE_UNROLL
-    for (int i = 0; i < kQpN; i++) zmax = fmax(zmax, fabs(z[i]));
-    const TC ptol = 1e-8 * zmax;
-    // multipliers of the own rows: s_i = g_i + sum_j G_ij z_j
-    TC mult[4];
     CASSIE_UNROLL
     for (int s = 0; s < 4; s++) {
       const int i = 4 * s + l;
-      const bool valid = i < kQpN;
-      TC acc = TC(0);
-      CASSIE_UNROLL
-      for (int j = 0; j < kQpN; j++) acc += (valid ? G[qtri(i, j)] : TC(0)) * z[j];
-      TC gi = TC(0);
-      CASSIE_UNROLL
-      for (int j = 0; j < kQpN; j++) gi = (j == i) ? gv[j] : gi;
-      mult[s] = gi + acc;
+      if (s < 3 || has3) zb[i] = ((at_lo >> i) & 1u) ? lo_own[s] : (((at_hi >> i) & 1u) ? hi_own[s] : TC(0));
     }
-    unsigned viol = 0u;
+    wsync();
+    QpRegs R;
+    // masked KKT matrix (own rows, in registers) and right-hand side: rhs_i = pinned ? bound : -(g_i + sum_j G_ij zB_j)
+    CASSIE_UNROLL
+    for (int s = 0; s < 4; s++) {
+      const int i = 4 * s + l;
+      const bool pin = ((fixed >> i) & 1u) != 0u || i >= N;
+      TC acc = TC(0), zbi = TC(0);
+      CASSIE_UNROLL
+      for (int j = 0; j < N; j++) {
+        const TC gij = Grow[s][j];
+        const TC zbj = zb[j];
+        acc += gij * zbj;
+        zbi = (j == i) ? zbj : zbi;
+        if (j <= 4 * s + 3) {
+          const TC kij = (pin || ((fixed >> j) & 1u)) ? (i == j ? TC(1) : TC(0)) : gij;
+          if (s == 0) R.L0[j < 4 ? j : 3] = kij;
+          else if (s == 1) R.L1[j < 8 ? j : 7] = kij;
+          else if (s == 2) R.L2[j < 12 ? j : 11] = kij;
+          else R.L3[j < 14 ? j : 13] = kij;
+        }
+      }
+      R.rhs[s] = pin ? zbi : -(g_own[s] + acc);
+    }
+    bool ok = true;
+    QpPivot<0>::run(R, ln, col, ok);
+    QpForward<0>::run(R, ln);
+    QpBackward<N - 1>::run(R, ln);
+    // multipliers of the own rows: s_i = g_i + sum_j G_ij z_j
+    CASSIE_UNROLL
+    for (int s = 0; s < 4; s++) {
+      const int i = 4 * s + l;
+      if (s < 3 || has3) {
+        TC acc = g_own[s];
+        CASSIE_UNROLL
+        for (int j = 0; j < N; j++) acc += Grow[s][j] * R.z[j];
+        mult[i] = acc;
+      }
+    }
+    wsync();
+    // ---- violations: free variables outside their bounds, pinned variables with a wrong-sign multiplier (osc_qp.cuh)
+    TC zmax = 1.0;
+    CASSIE_UNROLL
+    for (int i = 0; i < N; i++) zmax = fmax(zmax, fabs(R.z[i]));
+    const TC ptol = 1e-8 * zmax;
+    unsigned viol = 0u, below = 0u;
     int nviol = 0, last = -1, worst = -1;
     TC worst_mag = -1.0;
     CASSIE_UNROLL
-    for (int i = 0; i < kQpN; i++) {
+    for (int i = 0; i < N; i++) {
+      const TC lo_i = i < kNU ? m.act_lo[i < kNU ? i : 0] : TC(0), hi_i = i < kNU ? m.act_hi[i < kNU ? i : 0] : TC(1e30);
+      const TC zi = R.z[i];
       TC v, mag;
       bool bad;
-      const TC si = shfl(mult[i / 4], i % 4);
       if ((fixed >> i) & 1u) {
+        const TC si = mult[i];
         v = ((at_lo >> i) & 1u) ? -si : si;
         bad = v > dtol;
         mag = v / gscale;
       } else {
-        v = fmax(lo[i] - z[i], z[i] - hi[i]);
+        v = fmax(lo_i - zi, zi - hi_i);
         bad = v > ptol;
         mag = v / zmax;
       }
+      if (zi < lo_i) below |= 1u << i;
       if (bad) {
         viol |= 1u << i; nviol++; last = i;
         if (mag > worst_mag) { worst_mag = mag; worst = i; }
       }
     }
     if (!fin) {
-      CASSIE_UNROLL
-      for (int i = 0; i < kQpN; i++) zf[i] = z[i];
+      if (l == 0) {
+        CASSIE_UNROLL
+        for (int i = 0; i < kNU; i++) zfin[i] = R.z[i];
+      }
       if (!ok) { status = 2; fin = true; }
       else if (nviol == 0) { status = 0; it++; fin = true; }
       else {
         if (nviol < best) best = nviol;
         else viol = 1u << (it < kQpGreedyIters ? worst : last);
-        CASSIE_UNROLL
-        for (int i = 0; i < kQpN; i++) {
-          if (!((viol >> i) & 1u)) continue;
-          if ((fixed >> i) & 1u) { at_lo &= ~(1u << i); at_hi &= ~(1u << i); }
-          else if (z[i] < lo[i]) at_lo |= 1u << i;
-          else at_hi |= 1u << i;
-        }
+        const unsigned rel = viol & fixed, pinv = viol & ~fixed;   // pinned violators are released, free ones pinned
+        at_lo = (at_lo & ~rel) | (pinv & below);
+        at_hi = (at_hi & ~rel) | (pinv & ~below);
         it++;
       }
     }
     if (!wany(!fin)) break;
   }
+  wsync();
   CASSIE_UNROLL
-  for (int i = 0; i < kQpN; i++) z[i] = zf[i] < lo[i] ? lo[i] : (zf[i] > hi[i] ? hi[i] : zf[i]);
+  for (int i = 0; i < kNU; i++) {   // only the motor commands leave the QP
+    const TC lo_i = m.act_lo[i], hi_i = m.act_hi[i];
+    const TC zi = zfin[i];
+    z[i] = zi < lo_i ? lo_i : (zi > hi_i ? hi_i : zi);
+  }
   if (st) { st->iters = it; st->status = status; }
 }
 
@@ -582,17 +645,17 @@ QUAD_FN void quad_osc(const PlanarModel<TC>& m, const Lane ln, const LegKin<TC>&
           if (j == i + 1) v1 += kOscWForce * (kOscMu * kOscMu + 1.0);
           if (j == i) v1 += kOscWForce * (1.0 - kOscMu * kOscMu);
         }
-        if (j <= i) G[qtri(i, j)] = v0;
-        G[qtri(i + 1, j)] = v1;
+        if (j <= i) { G[i * kQpN + j] = v0; G[j * kQpN + i] = v0; }
+        G[(i + 1) * kQpN + j] = v1; G[j * kQpN + i + 1] = v1;
       }
     }
   }
   wsync();
   // ---- the box QP, cooperatively (quad_box_qp)
   {
-    TC z[kQpN];
+    TC z[kNU];
     unsigned at_lo = qp_set & 0x3fffu, at_hi = (qp_set >> 14) & 0x3fu;
-    quad_box_qp(ln, C.at(Y::G), C.at(Y::g), m, z, at_lo, at_hi, 300, st);
+    quad_box_qp(ln, C.at(Y::G), C.at(Y::g), C.at(Y::qpv), m, z, at_lo, at_hi, 300, st);
     qp_set = at_lo | (at_hi << 14);
     if (ln.ql == 0) {
       CASSIE_UNROLL

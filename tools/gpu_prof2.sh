@@ -8,7 +8,7 @@ for spec in "$@"; do
   IFS=: read wl kr pre <<< "$spec"
   echo "== bench $wl pre=$pre"; timeout 300 python bench.py --workload $wl --steps 20 --warmup 3 --preadvance $pre --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/${TAG}_bench_${wl}.json | cut -c1-300
   echo "== ncu $wl $kr"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$kr -s 3 -c 1 -f -o /tmp/${TAG}_${wl} \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$kr -s ${SKIP:-3} -c 1 -f -o /tmp/${TAG}_${wl} \
     python bench.py --workload $wl --steps 2 --warmup 1 --preadvance $pre --no-cpu-baseline > gpurun_out/${TAG}_${wl}_ncu.log 2>&1
   tail -2 gpurun_out/${TAG}_${wl}_ncu.log | cut -c1-200
   python tools/summarize_ncu.py /tmp/${TAG}_${wl}.ncu-rep > gpurun_out/${TAG}_${wl}.txt 2>&1
