@@ -542,6 +542,7 @@ QUAD_FN void quad_osc(const PlanarModel<TC>& m, const Lane ln, const LegKin<TC>&
     C[Y::e0 + 11] = TC(0);
   }
   quad_ctrl_dynamics(m, ln, k, qd, C, d);   // ends with every lane past the barrier that publishes task rows and e0
+  phase_sync<2>();
   // ---- task loop: half h takes the six tasks of leg h (h = 0: body x, body z, left sites; h = 1: pitch, padding,
   // right sites).  Z_r = Mc^-1 A_r' = M^-1 (A_r' - Jeq' P JH A_r'); E_r = Z_r' [Bt, Jc' T]; r0_r = Jdot qd - xdd* + A_r p0
   TC Js[2][2][8];   // own leg's two sites (x, z rows): the contact generators of this leg
@@ -611,6 +612,7 @@ QUAD_FN void quad_osc(const PlanarModel<TC>& m, const Lane ln, const LegKin<TC>&
     }
   }
   wsync();
+  phase_sync<2>();
   // ---- G = 2 E'WE (packed lower triangle), g = 2 E'W r0 (OSC_RBDL.cpp:186-203): lane l builds the row pairs l and 6 - l
   {
     const SV<TC> G = C.at(Y::G), g = C.at(Y::g);
@@ -651,6 +653,7 @@ QUAD_FN void quad_osc(const PlanarModel<TC>& m, const Lane ln, const LegKin<TC>&
     }
   }
   wsync();
+  phase_sync<2>();
   // ---- the box QP, cooperatively (quad_box_qp)
   {
     TC z[kNU];
@@ -790,6 +793,7 @@ QUAD_FN void quad_controller_step(const PlanarModel<T>& mphys, const PlanarModel
     }
   }
   wsync();
+  phase_sync<1>();
   quad_physics_step(mphys, mphys_g, ln, St, Wp, st);
 }
 

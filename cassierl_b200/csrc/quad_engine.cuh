@@ -553,9 +553,14 @@ QUAD_FN int quad_pgs(const PlanarModel<T>& m, const Lane ln, const T (&A)[Tier<T
   }
   int iter = 0, done_at = 0;
   bool done = false;
-  T g[KO];   // snapshot of the forces at the sweep where this env converged
+  T g[KO], fprev[KO];   // forces at the sweep where this env converged; forces after the previous sweep
   CASSIE_UNROLL
-  for (int k = 0; k < KO; k++) g[k] = T(0);
+  for (int k = 0; k < KO; k++) { g[k] = T(0); fprev[k] = f[k]; }
+  // The convergence test of mj_solPGS runs ONE SWEEP LATE: the quad-wide sum of a sweep's cost improvement (two
+  // shuffles) is issued at the end of the sweep and consumed at the end of the next one, so that its latency sits under
+  // the next sweep instead of on the loop's critical path.  A converged env is detected one sweep after the fact: its
+  // forces were snapshotted (fprev), the extra sweep is discarded.
+  T imp_prev = T(1e30);
   while (true) {
     T so[KO], cres[KO];   // forces at the start of the sweep (= "old" of the own slots), residuals seen by the own slots
     CASSIE_UNROLL
@@ -604,7 +609,19 @@ QUAD_FN int quad_pgs(const PlanarModel<T>& m, const Lane ln, const T (&A)[Tier<T
       acc[NSL + 1] = (own ? b[NSL + 1] : acc[NSL + 1]) + A[NSL + 1][i] * (own ? T(0) : F0);   // own: row i + 1 skips column i
       acc[NSL + 1] += A[NSL + 1][i + 1] * F1;                                 // own: A = A_tt
     }
+    // verdict on the PREVIOUS sweep (its improvement has had a whole sweep to arrive)
+    if (!done && iter >= 1 && imp_prev * scale < m.tolerance) {
+      done = true; done_at = iter;
+      CASSIE_UNROLL
+      for (int k = 0; k < KO; k++) g[k] = fprev[k];
+    }
     iter++;
+    if (!done && iter >= m.iterations) {
+      done = true; done_at = iter;
+      CASSIE_UNROLL
+      for (int k = 0; k < KO; k++) g[k] = f[k];
+    }
+    if (!wany(!done)) break;
     // once per sweep, on the own rows: ray denominator of the own pair for the next sweep, cost improvement
     {
       const T f1 = f[NSL], f2 = f[NSL + 1];
@@ -622,14 +639,9 @@ QUAD_FN int quad_pgs(const PlanarModel<T>& m, const Lane ln, const T (&A)[Tier<T
       improvement -= d0 * (T(0.5) * d0 * App + Apt * d1 + cres[NSL]) + d1 * (T(0.5) * d1 * Att + cres[NSL + 1]);
     }
     T imp = improvement + shx(improvement, 1);
-    imp = imp + shx(imp, 2);
-    const bool conv = imp * scale < m.tolerance;
-    if (!done && (conv || iter >= m.iterations)) {
-      done = true; done_at = iter;
-      CASSIE_UNROLL
-      for (int k = 0; k < KO; k++) g[k] = f[k];
-    }
-    if (!wany(!done)) break;
+    imp_prev = imp + shx(imp, 2);
+    CASSIE_UNROLL
+    for (int k = 0; k < KO; k++) fprev[k] = f[k];
   }
   CASSIE_UNROLL
   for (int k = 0; k < KO; k++) fout[k] = g[k];
@@ -810,12 +822,14 @@ QUAD_FN void quad_constraints(const PlanarModel<T>& m, const Lane ln, SV<T> S, c
   }
 
   // ---- PGS
+  phase_sync<2>();
   T fown[KO];
   int sweeps;
   if (narrow) sweeps = quad_pgs<TIER, 1>(m, ln, A, bown, jar, Rown, fown);
   else sweeps = quad_pgs<TIER, 2>(m, ln, A, bown, jar, Rown, fown);
 
   // ---- qfrc_constraint = J^T f over the slots of this leg (own rows + the partner's)
+  phase_sync<2>();
   {
     T pb[3] = {T(0), T(0), T(0)};
     CASSIE_UNROLL
@@ -941,6 +955,7 @@ QUAD_FN void quad_physics_step(const PlanarModel<T>& m, const PlanarModel<TG>& m
       if (m.act_dof[a] == 3 + 5 * L + i) fs.l[i] += m.act_gear[a] * c;
   }
   wsync();   // both factors are in shared memory
+  phase_sync<2>();
 
   // ---- qacc_smooth
   V8<T> qs = fs;

@@ -10,11 +10,18 @@ namespace cassie {
 namespace quad {
 
 constexpr int kEnvsPerWarp = 8;
+// Warps per CTA.  The physics-only modes run one warp per CTA (fourteen independent CTAs per SM); the controller modes
+// run all the warps an SM can hold (seven, shared memory bound) as ONE CTA kept in lock step by a barrier per simulator
+// step: their once-per-step code is straight-line and several times the size of the instruction cache, and in lock step
+// one fill serves seven warps (profiles/r2k: squat_jacobian +27 %, squat_osc +8 %; pd_env -6 % with the barrier).
 #ifndef CASSIE_QUAD_WARPS
 #define CASSIE_QUAD_WARPS 1
 #endif
-constexpr int kQuadWarps = CASSIE_QUAD_WARPS;
-constexpr int kQuadBlock = 32 * kQuadWarps;
+#ifndef CASSIE_QUAD_WARPS_CTRL
+#define CASSIE_QUAD_WARPS_CTRL 7
+#endif
+constexpr int quad_warps(int mode) { return mode >= kModeJacobian ? CASSIE_QUAD_WARPS_CTRL : CASSIE_QUAD_WARPS; }
+constexpr int quad_block(int mode) { return 32 * quad_warps(mode); }
 
 // scratch bytes per env: the controller's block only exists in the Jacobian / OSC modes
 template <typename T>
@@ -29,9 +36,16 @@ constexpr size_t warp_bytes(int mode) {
 // resident CTAs per SM the register allocation is sized for (228 KB of shared memory per SM, 1 KB reserved per CTA)
 template <typename T>
 constexpr int min_blocks(int mode) {
-  const size_t per = kQuadWarps * warp_bytes<T>(mode) + 1024;
+  const size_t per = quad_warps(mode) * warp_bytes<T>(mode) + 1024;
   const int b = (int)((228 * 1024) / per);
   return b > 14 ? 14 : (b < 1 ? 1 : b);   // 16384 envs = 13.8 warps per SM: more resident slots than that only cost registers
+}
+
+// several warps per CTA (CASSIE_QUAD_WARPS): a barrier per simulator step keeps them in the same code region, so that
+// one instruction-cache fill serves all of them (the once-per-step code is straight-line and far larger than the I-cache)
+template <int MODE>
+__device__ __forceinline__ void step_sync() {
+  if (quad_warps(MODE) > 1) __syncthreads();
 }
 
 struct QuadEnv {
@@ -39,12 +53,12 @@ struct QuadEnv {
   bool active;
   Lane ln;
 };
-template <typename T>
+template <int MODE, typename T>
 __device__ __forceinline__ QuadEnv quad_env(const BatchView<T>& v) {
   QuadEnv q;
   const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
   q.ei = lane >> 2;
-  const int e_raw = ((int)blockIdx.x * kQuadWarps + warp) * kEnvsPerWarp + q.ei;
+  const int e_raw = ((int)blockIdx.x * quad_warps(MODE) + warp) * kEnvsPerWarp + q.ei;
   q.active = e_raw < v.n;      // inactive quads shadow the last env (they take part in the warp collectives)
   q.e = q.active ? e_raw : v.n - 1;
   q.ln = lane_id();
@@ -93,9 +107,9 @@ __device__ __forceinline__ void quad_step(const ModelPair<T>& mp, const QuadEnv&
 // ---------------------------------------------------------------------------------------
 // n_substeps x Step* (Cassie2d.cpp:86-209) with a held action
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kQuadBlock, min_blocks<T>(MODE))
+__global__ void __launch_bounds__(quad_block(MODE), min_blocks<T>(MODE))
 k_qstep(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v, const T* __restrict__ action, int n_sub, uint32_t* mask) {
-  const QuadEnv qe = quad_env(v);
+  const QuadEnv qe = quad_env<MODE>(v);
   unsigned char* wb = warp_smem<T, MODE>();
   const SV<T> St{reinterpret_cast<T*>(wb) + qe.ei};
   load_state(v, qe, St);
@@ -106,7 +120,10 @@ k_qstep(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v, const T* 
   QStepStats st = {0, 0, 0u};
   OscStats qs = {0, 0};
   unsigned qps = v.qp_set[qe.e];
-  for (int s = 0; s < n_sub; s++) quad_step<T, MODE>(mp, qe, St, wb, act, s == n_sub - 1, &st, &qs, &qps);
+  for (int s = 0; s < n_sub; s++) {
+    step_sync<MODE>();
+    quad_step<T, MODE>(mp, qe, St, wb, act, s == n_sub - 1, &st, &qs, &qps);
+  }
   store_state(v, qe, St);
   if (qe.active && qe.ln.ql == 0) {
     v.qp_set[qe.e] = qps;
@@ -120,9 +137,9 @@ k_qstep(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v, const T* 
 // ---------------------------------------------------------------------------------------
 // squatting.py:8-16 with standing_controller_jacobian / standing_controller_osc in the loop
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kQuadBlock, min_blocks<T>(MODE))
+__global__ void __launch_bounds__(quad_block(MODE), min_blocks<T>(MODE))
 k_qsquat(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v, const T* __restrict__ phase, int n_steps, uint32_t* mask) {
-  const QuadEnv qe = quad_env(v);
+  const QuadEnv qe = quad_env<MODE>(v);
   unsigned char* wb = warp_smem<T, MODE>();
   const SV<T> St{reinterpret_cast<T*>(wb) + qe.ei};
   load_state(v, qe, St);
@@ -133,6 +150,7 @@ k_qsquat(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v, const T*
   const double wq = 0.5 * 3.1415;  // squatting.py:9
   unsigned qps = v.qp_set[qe.e];
   for (int s = 0; s < n_steps; s++) {
+    step_sync<MODE>();
     T o18[18], act[7];
     quad_op_array(St, o18);
     double sn, cs;
@@ -159,10 +177,10 @@ k_qsquat(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v, const T*
 // One policy step of the Python env (cassie_stand2d.py:86-137 / cassie2d.py:97-225): the substeps by the quad, the
 // observation / reward / termination / auto-reset arithmetic (env_kernels.cuh env_finish) by its lane 0
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kQuadBlock, min_blocks<T>(MODE))
+__global__ void __launch_bounds__(quad_block(MODE), min_blocks<T>(MODE))
 k_qenv_step(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v, const __grid_constant__ EnvStepDev<T> a) {
   typedef StateLayout X;
-  const QuadEnv qe = quad_env(v);
+  const QuadEnv qe = quad_env<MODE>(v);
   unsigned char* wb = warp_smem<T, MODE>();
   const SV<T> St{reinterpret_cast<T*>(wb) + qe.ei};
   load_state(v, qe, St);
@@ -175,6 +193,7 @@ k_qenv_step(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v, const
   double t = v.clock[qe.e];
   unsigned qps = v.qp_set[qe.e];
   for (int s = 0; s < a.n_sub; s++) {
+    step_sync<MODE>();
     quad_step<T, MODE>(mp, qe, St, wb, act, s == a.n_sub - 1, &st, &qs, &qps);
     t += 0.0005;  // cassie2d.py:122
   }
@@ -200,30 +219,32 @@ k_qenv_step(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v, const
 
 // ---------------------------------------------------------------------------------------
 template <typename K>
-inline void prefer_shared(K kernel) {
+inline void prefer_shared(K kernel, size_t dyn_bytes) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (dyn_bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes);
 }
-inline unsigned quad_grid(int n) { return (unsigned)((n + kEnvsPerWarp * kQuadWarps - 1) / (kEnvsPerWarp * kQuadWarps)); }
+
+inline unsigned quad_grid(int n, int mode) { return (unsigned)((n + kEnvsPerWarp * quad_warps(mode) - 1) / (kEnvsPerWarp * quad_warps(mode))); }
 
 template <typename T, int MODE>
 inline cudaError_t launch_qstep(const ModelPair<T>& mp, const BatchView<T>& v, const T* act, int n_sub, uint32_t* mask, cudaStream_t s) {
-  static bool once = (prefer_shared(k_qstep<T, MODE>), true);
+  static bool once = (prefer_shared(k_qstep<T, MODE>, quad_warps(MODE) * warp_bytes<T>(MODE)), true);
   (void)once;
-  k_qstep<T, MODE><<<quad_grid(v.n), kQuadBlock, kQuadWarps * warp_bytes<T>(MODE), s>>>(mp, v, act, n_sub, mask);
+  k_qstep<T, MODE><<<quad_grid(v.n, MODE), quad_block(MODE), quad_warps(MODE) * warp_bytes<T>(MODE), s>>>(mp, v, act, n_sub, mask);
   return cudaGetLastError();
 }
 template <typename T, int MODE>
 inline cudaError_t launch_qsquat(const ModelPair<T>& mp, const BatchView<T>& v, const T* phase, int n_steps, uint32_t* mask, cudaStream_t s) {
-  static bool once = (prefer_shared(k_qsquat<T, MODE>), true);
+  static bool once = (prefer_shared(k_qsquat<T, MODE>, quad_warps(MODE) * warp_bytes<T>(MODE)), true);
   (void)once;
-  k_qsquat<T, MODE><<<quad_grid(v.n), kQuadBlock, kQuadWarps * warp_bytes<T>(MODE), s>>>(mp, v, phase, n_steps, mask);
+  k_qsquat<T, MODE><<<quad_grid(v.n, MODE), quad_block(MODE), quad_warps(MODE) * warp_bytes<T>(MODE), s>>>(mp, v, phase, n_steps, mask);
   return cudaGetLastError();
 }
 template <typename T, int MODE>
 inline cudaError_t launch_qenv_step(const ModelPair<T>& mp, const BatchView<T>& v, const EnvStepDev<T>& d, cudaStream_t s) {
-  static bool once = (prefer_shared(k_qenv_step<T, MODE>), true);
+  static bool once = (prefer_shared(k_qenv_step<T, MODE>, quad_warps(MODE) * warp_bytes<T>(MODE)), true);
   (void)once;
-  k_qenv_step<T, MODE><<<quad_grid(v.n), kQuadBlock, kQuadWarps * warp_bytes<T>(MODE), s>>>(mp, v, d);
+  k_qenv_step<T, MODE><<<quad_grid(v.n, MODE), quad_block(MODE), quad_warps(MODE) * warp_bytes<T>(MODE), s>>>(mp, v, d);
   return cudaGetLastError();
 }
 

@@ -109,6 +109,18 @@ template <typename F> inline void run_quad(F fn) {
 }
 #endif
 
+// Phase barrier of a multi-warp CTA (quad_kernels.cuh): keeps the warps of a CTA in the same code region so that they
+// share instruction-cache fills.  LEVEL = how fine a grain the call site is; CASSIE_QUAD_PHASE_SYNC selects up to which
+// level barriers are compiled in (0: only the per-step barrier of the kernels).
+#ifndef CASSIE_QUAD_PHASE_SYNC
+#define CASSIE_QUAD_PHASE_SYNC 0
+#endif
+template <int LEVEL> QUAD_FN void phase_sync() {
+#if defined(__CUDACC__)
+  if (LEVEL <= CASSIE_QUAD_PHASE_SYNC && blockDim.x > 32) __syncthreads();
+#endif
+}
+
 // view of one env's column of an [n][kES] shared array
 template <typename V>
 struct SV {
