@@ -1,9 +1,8 @@
-// Engine selection for the three step launches.  Two complete engines live in this library:
-//   quad    (default) four lanes per env, shared-memory scratch  -- quad_engine.cuh, quad_ctrl.cuh, quad_kernels.cuh
-//   thread  one env per thread, thread-local scratch (round 1)   -- planar_engine.cuh ... env_kernels.cuh
-// CASSIE_ENGINE=thread|quad picks one at process start; a batch of fewer than kQuadMinEnvs envs (the legacy batch-of-one
-// ABI) always runs the thread engine.  Both are checked against the oracle by the same tests (tests/test_gpu_*.py run
-// once per engine).
+// Engine selection for the step launches.  Two complete engines live in this library:
+//   quad    four lanes per env, shared-memory scratch        -- quad_engine.cuh, quad_ctrl.cuh, quad_kernels.cuh
+//   thread  one env per thread, thread-local scratch (round 1) -- planar_engine.cuh ... env_kernels.cuh
+// A batch of fewer than kQuadMinEnvs envs (the legacy batch-of-one ABI) always runs the thread engine.  Both engines
+// are checked against the oracle by the same tests (tests/test_gpu_engines.py re-runs the parity files per engine).
 #pragma once
 #include <cstdlib>
 #include <cstring>
@@ -12,17 +11,27 @@
 namespace cassie {
 
 constexpr int kQuadMinEnvs = 2;
-inline bool engine_is_quad() {
-  static const bool quad = [] {
+// CASSIE_ENGINE = quad | thread forces one engine for every mode; unset = the measured default per control mode
+// (profiles/r2_engines.txt): the quad engine for the controller modes (Jacobian, OSC), the thread engine for the
+// physics-only modes (torque, PD), where robots thrown around by random actions spend their time in the general
+// constraint tier that the quad engine steps serially.
+inline int engine_choice() {
+  static const int c = [] {
     const char* e = getenv("CASSIE_ENGINE");
-    return !(e && strcmp(e, "thread") == 0);
+    if (e && strcmp(e, "thread") == 0) return 0;
+    if (e && strcmp(e, "quad") == 0) return 1;
+    return 2;
   }();
-  return quad;
+  return c;
+}
+inline bool engine_for_mode(int mode) {
+  const int c = engine_choice();
+  return c == 1 || (c == 2 && mode >= kModeJacobian);
 }
 
 template <typename T>
 cudaError_t Launch<T>::step(const ModelPair<T>& mp, const BatchView<T>& v, const StepArgs& a, cudaStream_t s) {
-  if (!engine_is_quad() || v.n < kQuadMinEnvs) return thread_step<T>(mp, v, a, s);
+  if (!engine_for_mode(a.mode) || v.n < kQuadMinEnvs) return thread_step<T>(mp, v, a, s);
   const T* act = (const T*)a.action;
   cudaError_t e;
   switch (a.mode) {
@@ -38,7 +47,7 @@ cudaError_t Launch<T>::step(const ModelPair<T>& mp, const BatchView<T>& v, const
 
 template <typename T>
 cudaError_t Launch<T>::env_step(const ModelPair<T>& mp, const BatchView<T>& v, const EnvStepArgs& a, cudaStream_t s) {
-  if (!engine_is_quad() || v.n < kQuadMinEnvs) return thread_env_step<T>(mp, v, a, s);
+  if (!engine_for_mode(a.mode) || v.n < kQuadMinEnvs) return thread_env_step<T>(mp, v, a, s);
   const EnvStepDev<T> d = make_env_step_dev<T>(a);
   cudaError_t e;
   switch (a.mode) {
@@ -53,7 +62,7 @@ cudaError_t Launch<T>::env_step(const ModelPair<T>& mp, const BatchView<T>& v, c
 
 template <typename T>
 cudaError_t Launch<T>::squat(const ModelPair<T>& mp, const BatchView<T>& v, const SquatArgs& a, cudaStream_t s) {
-  if (!engine_is_quad() || v.n < kQuadMinEnvs) return thread_squat<T>(mp, v, a, s);
+  if (!engine_for_mode(a.mode) || v.n < kQuadMinEnvs) return thread_squat<T>(mp, v, a, s);
   cudaError_t e;
   if (a.mode == kModeJacobian) e = quad::launch_qsquat<T, kModeJacobian>(mp, v, (const T*)a.phase, a.n_steps, a.contact_mask, s);
   else if (a.mode == kModeOsc) e = quad::launch_qsquat<T, kModeOsc>(mp, v, (const T*)a.phase, a.n_steps, a.contact_mask, s);

@@ -460,6 +460,10 @@ QUAD_FN void load_v8(SV<T> s, int L, V8<T>& x) {
 // profiles/r2c_pd_env.txt, 13 of 32 threads active in the publish code of the first cut).  The owner's rows restart
 // their residual (acc = b + A_own f_own) through the same FMA that adds the column to everybody else's rows, with the
 // accumulator input swapped for b; row i + 1 of a pair skips column i (planar_engine.cuh).
+// NCL = contact slots per leg in use anywhere in the warp: with 1, only the pairs of lanes 0 and 2 are visited (the others
+// are inert in every env of the warp, their contribution is an exact zero).  A run-time, warp-uniform mask that skips
+// every unused slot individually was measured slower (r2n: squat_osc -9 %, pd_env -18 %): the branches break up the
+// schedule of the unrolled sweep.
 template <int TIER, int NCL, typename T>
 QUAD_FN int quad_pgs(const PlanarModel<T>& m, const Lane ln, const T (&A)[Tier<TIER>::KO][Tier<TIER>::NR],
                      const T (&b)[Tier<TIER>::KO], const T (&jar)[Tier<TIER>::KO], const T (&Rr)[Tier<TIER>::KO],

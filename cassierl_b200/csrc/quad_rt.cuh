@@ -44,6 +44,12 @@ QUAD_FN bool qany(bool p) {
   const unsigned b = __ballot_sync(0xffffffffu, p);
   return ((b >> ((threadIdx.x & 31u) & ~3u)) & 0xfu) != 0u;
 }
+// 4-bit mask: bit c is set when lane position c of ANY quad of the warp has p (warp uniform)
+QUAD_FN unsigned wlanes(bool p) {
+  unsigned b = __ballot_sync(0xffffffffu, p);
+  b |= b >> 16; b |= b >> 8; b |= b >> 4;
+  return b & 0xfu;
+}
 
 #else  // ------------------------------------------------------------------ host emulation (one quad)
 constexpr int kES = 1;
@@ -101,6 +107,14 @@ QUAD_FN bool wany(bool p) {
   return r;
 }
 QUAD_FN bool qany(bool p) { return wany(p); }
+QUAD_FN unsigned wlanes(bool p) {
+  Emu& e = emu();
+  e.pred[emu_lane()] = p;
+  e.barrier();
+  const unsigned r = (e.pred[0] ? 1u : 0u) | (e.pred[1] ? 2u : 0u) | (e.pred[2] ? 4u : 0u) | (e.pred[3] ? 8u : 0u);
+  e.barrier();
+  return r;
+}
 // runs fn(lane) on four threads
 template <typename F> inline void run_quad(F fn) {
   std::thread th[4];

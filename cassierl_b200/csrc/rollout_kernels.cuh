@@ -349,7 +349,7 @@ cudaError_t launch_advantages(const BaselineArgs& a, cudaStream_t s) {
 }
 
 template <typename T>
-cudaError_t launch_rollout(const ModelPair<T>& mp, const BatchView<T>& v, const RolloutArgs& a, cudaStream_t s) {
+RolloutDev<T> make_rollout_dev(const RolloutArgs& a) {
   RolloutDev<T> d;
   d.task = a.task; d.flags = a.flags; d.n_sub = a.n_substeps; d.T_steps = a.T_steps; d.max_path_length = a.max_path_length;
   d.normalize = a.normalize; d.seed = a.seed; d.env0 = a.env0;
@@ -359,6 +359,12 @@ cudaError_t launch_rollout(const ModelPair<T>& mp, const BatchView<T>& v, const 
                          0.0, 0.0, 0.0, 0.0, 0.0, 0.68111815, -1.40730357, 1.62972042, -1.77611107, -0.61968407,
                          0.0, 0.0, 0.0, 0.0, 0.0};
   for (int i = 0; i < 26; i++) d.reset_state[i] = (T)qi[i];
+  return d;
+}
+// thread-per-env launcher (rollout_launch.cuh picks between this and the quad engine's)
+template <typename T>
+cudaError_t thread_rollout(const ModelPair<T>& mp, const BatchView<T>& v, const RolloutArgs& a, cudaStream_t s) {
+  const RolloutDev<T> d = make_rollout_dev<T>(a);
   const int odim = a.task == kTaskStand ? 17 : 26, adim = action_dim(a.mode);
   const int n_params = odim * kHidden + kHidden + kHidden * kHidden + kHidden + kHidden * adim + adim + adim;
   const size_t smem = sizeof(T) * (size_t)(n_params + 26 * kBlock);
