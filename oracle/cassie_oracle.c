@@ -4,6 +4,9 @@
  * Part 2 (cassie_oracle_ctrl.c): RBDL-equivalent getters, controllers, Cassie2d facade.
  */
 #include "cassie_oracle_internal.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 /* ------------------------------------------------------------------ small vector helpers */
 void orc_mat3_mulv(double r[3], const double M[9], const double v[3]) {
@@ -138,7 +141,28 @@ int orc_add_body(orc_model* m, int parent, const double pos[3], const double mat
 int orc_add_joint(orc_model* m, int body, int type, const double axis[3], const double pos[3],
                   double ref, int limited, const double range[2], double damping,
                   double armature, const double solref[2], const double solimp[5]) {
+  if (type == ORC_JNT_FREE) {
+    /* mjJNT_FREE [EXT]: dofs = world-axis translations then body-axis rotations, qpos = pos(3) + quat(4) */
+    int first = m->nv;
+    for (int k = 0; k < 6; k++) {
+      int j = m->nv++;
+      memset(m->jnt_axis[j], 0, 24);
+      m->jnt_axis[j][k % 3] = 1.0;
+      memset(m->jnt_pos[j], 0, 24);
+      m->jnt_body[j] = body; m->jnt_type[j] = k < 3 ? ORC_JNT_FREE_T : ORC_JNT_FREE_R;
+      m->jnt_qadr[j] = m->nq + (k < 3 ? k : 3);   /* rotations: address of the quaternion */
+      m->jnt_ref[j] = 0; m->jnt_limited[j] = 0;
+      m->jnt_damping[j] = damping; m->jnt_armature[j] = armature;
+      memcpy(m->jnt_solref[j], solref, 16);
+      memcpy(m->jnt_solimp[j], solimp, 40);
+      if (m->body_jntnum[body] == 0) m->body_jntadr[body] = j;
+      m->body_jntnum[body]++;
+    }
+    m->nq += 7;
+    return first;
+  }
   int j = m->nv++;
+  m->jnt_qadr[j] = m->nq++;
   m->jnt_body[j] = body; m->jnt_type[j] = type;
   memcpy(m->jnt_axis[j], axis, 24);
   normalize3(m->jnt_axis[j]);
@@ -191,6 +215,7 @@ void orc_set_option(orc_model* m, double timestep, int iterations, double tolera
   m->impratio = impratio; memcpy(m->gravity, gravity, 24);
 }
 int orc_nv(const orc_model* m) { return m->nv; }
+int orc_nq(const orc_model* m) { return m->nq; }
 int orc_nbody(const orc_model* m) { return m->nbody; }
 double orc_total_mass(const orc_model* m) {
   double s = 0;
@@ -218,7 +243,8 @@ void orc_kin_update(const orc_model* m, orc_kin* k, const double* q, const doubl
   k->xmat[0][0] = k->xmat[0][4] = k->xmat[0][8] = 1;
   memset(k->V[0], 0, 48);
   memset(k->A[0], 0, 48);
-  for (int i = 0; i < m->nv; i++) { k->q[i] = q[i]; k->qd[i] = qd ? qd[i] : 0.0; }
+  for (int i = 0; i < m->nq; i++) k->q[i] = q[i];
+  for (int i = 0; i < m->nv; i++) k->qd[i] = qd ? qd[i] : 0.0;
   for (int b = 1; b < m->nbody; b++) {
     int p = m->body_parent[b];
     double pos[3], mat[9], t[3];
@@ -235,11 +261,46 @@ void orc_kin_update(const orc_model* m, orc_kin* k, const double* q, const doubl
       orc_mat3_mulv(t, mat, m->jnt_pos[j]);
       for (int i = 0; i < 3; i++) an[i] = pos[i] + t[i];
       double* S = k->S[j];
+      const int qa = m->jnt_qadr[j];
+      if (m->jnt_type[j] == ORC_JNT_FREE_T) {
+        /* mj_kinematics [EXT]: a free body's frame IS its qpos (the model's body pos is only qpos0) */
+        int c = j - m->body_jntadr[b];
+        S[0] = S[1] = S[2] = S[3] = S[4] = S[5] = 0;
+        S[3 + c] = 1.0;
+        pos[c] = q[qa];
+        double Sd0[6];
+        crm(Sd0, V, S);
+        for (int i = 0; i < 6; i++) { A[i] += Sd0[i] * k->qd[j]; V[i] += S[i] * k->qd[j]; }
+        continue;
+      }
+      if (m->jnt_type[j] == ORC_JNT_FREE_R) {
+        /* the three rotational dofs at once (mj_comVel [EXT]: all three cdof_dot use the velocity BEFORE the
+         * rotational part is added) */
+        double w = q[qa], x = q[qa + 1], y = q[qa + 2], z = q[qa + 3];
+        double nq = sqrt(w * w + x * x + y * y + z * z);
+        w /= nq; x /= nq; y /= nq; z /= nq;   /* mj_normalizeQuat */
+        mat[0] = 1 - 2 * (y * y + z * z); mat[1] = 2 * (x * y - w * z); mat[2] = 2 * (x * z + w * y);
+        mat[3] = 2 * (x * y + w * z); mat[4] = 1 - 2 * (x * x + z * z); mat[5] = 2 * (y * z - w * x);
+        mat[6] = 2 * (x * z - w * y); mat[7] = 2 * (y * z + w * x); mat[8] = 1 - 2 * (x * x + y * y);
+        double V0[6];
+        memcpy(V0, V, 48);
+        for (int c = 0; c < 3; c++) {
+          double* Sc = k->S[j + c];
+          double a3[3] = {mat[c], mat[3 + c], mat[6 + c]};
+          Sc[0] = a3[0]; Sc[1] = a3[1]; Sc[2] = a3[2];
+          orc_cross(Sc + 3, pos, a3);
+          double Sdc[6];
+          crm(Sdc, V0, Sc);
+          for (int i = 0; i < 6; i++) { A[i] += Sdc[i] * k->qd[j + c]; V[i] += Sc[i] * k->qd[j + c]; }
+        }
+        jj += 2;
+        continue;
+      }
       if (m->jnt_type[j] == ORC_JNT_HINGE) {
         S[0] = ax[0]; S[1] = ax[1]; S[2] = ax[2];
         orc_cross(S + 3, an, ax);
         double R[9];
-        axis_angle(R, ax, q[j] - m->jnt_ref[j]);
+        axis_angle(R, ax, q[qa] - m->jnt_ref[j]);
         double d[3] = {pos[0] - an[0], pos[1] - an[1], pos[2] - an[2]};
         orc_mat3_mulv(t, R, d);
         for (int i = 0; i < 3; i++) pos[i] = an[i] + t[i];
@@ -247,7 +308,7 @@ void orc_kin_update(const orc_model* m, orc_kin* k, const double* q, const doubl
       } else {
         S[0] = S[1] = S[2] = 0;
         S[3] = ax[0]; S[4] = ax[1]; S[5] = ax[2];
-        for (int i = 0; i < 3; i++) pos[i] += ax[i] * (q[j] - m->jnt_ref[j]);
+        for (int i = 0; i < 3; i++) pos[i] += ax[i] * (q[qa] - m->jnt_ref[j]);
       }
       /* Sdot = V_before x S ; A += Sdot*qd ; V += S*qd */
       double Sd[6];
@@ -383,7 +444,12 @@ int orc_compile(orc_model* m) {
       a = m->body_parent[a];
     }
   }
-  for (int i = 0; i < nv; i++) m->qpos0[i] = m->jnt_ref[i];
+  for (int i = 0; i < nv; i++) {
+    int qa = m->jnt_qadr[i];
+    if (m->jnt_type[i] == ORC_JNT_FREE_T) m->qpos0[qa] = m->body_pos[m->jnt_body[i]][i - m->body_jntadr[m->jnt_body[i]]];
+    else if (m->jnt_type[i] == ORC_JNT_FREE_R) { m->qpos0[qa] = 1.0; m->qpos0[qa + 1] = m->qpos0[qa + 2] = m->qpos0[qa + 3] = 0.0; }
+    else m->qpos0[qa] = m->jnt_ref[i];
+  }
   orc_kin* k = orc_kin_new();
   orc_kin_update(m, k, m->qpos0, NULL);
   /* connect: anchor2 = anchor1 expressed in body2 at qpos0 (mjCModel compile [EXT];
@@ -458,24 +524,26 @@ orc_model* orc_model_rbdl_variant(const orc_model* src) {
     orc_mat3_tmulv(m->eq_anchor2[e], k->xmat[b2], P);
   }
   orc_kin_free(k);
-  for (int i = 0; i < m->nv; i++) m->qpos0[i] = m->jnt_ref[i];
+  for (int i = 0; i < m->nv; i++) m->qpos0[m->jnt_qadr[i]] = m->jnt_ref[i];
   return m;
 }
 
 /* ------------------------------------------------------------------ data */
 orc_data* orc_data_new(const orc_model* m) {
   orc_data* d = (orc_data*)calloc(1, sizeof(orc_data));
-  d->nv = m->nv;
-  for (int i = 0; i < m->nv; i++) d->qpos[i] = m->qpos0[i];
+  d->nv = m->nv; d->nq = m->nq;
+  for (int i = 0; i < m->nq; i++) d->qpos[i] = m->qpos0[i];
   d->min_capsule_gap = 1e30;
   return d;
 }
 void orc_data_free(orc_data* d) { free(d); }
 void orc_set_state(orc_data* d, const double* qpos, const double* qvel) {
-  for (int i = 0; i < d->nv; i++) { d->qpos[i] = qpos[i]; d->qvel[i] = qvel[i]; }
+  for (int i = 0; i < d->nq; i++) d->qpos[i] = qpos[i];
+  for (int i = 0; i < d->nv; i++) d->qvel[i] = qvel[i];
 }
 void orc_get_state(const orc_data* d, double* qpos, double* qvel) {
-  for (int i = 0; i < d->nv; i++) { qpos[i] = d->qpos[i]; qvel[i] = d->qvel[i]; }
+  for (int i = 0; i < d->nq; i++) qpos[i] = d->qpos[i];
+  for (int i = 0; i < d->nv; i++) qvel[i] = d->qvel[i];
 }
 void orc_set_warmstart(orc_data* d, const double* w) { for (int i = 0; i < d->nv; i++) d->qacc_warmstart[i] = w[i]; }
 void orc_get_warmstart(const orc_data* d, double* w) { for (int i = 0; i < d->nv; i++) w[i] = d->qacc_warmstart[i]; }
@@ -518,7 +586,8 @@ static int plane_sphere(const double ppos[3], const double pn[3], const double c
   return 1;
 }
 
-static double seg_seg_dist(const double a0[3], const double a1[3], const double b0[3], const double b1[3]) {
+static double seg_seg_dist(const double a0[3], const double a1[3], const double b0[3], const double b1[3],
+                           double pa[3], double pb[3]) {
   /* closest distance between two segments (Ericson, Real-Time Collision Detection 5.1.9) */
   double d1[3], d2[3], r[3];
   for (int i = 0; i < 3; i++) { d1[i] = a1[i] - a0[i]; d2[i] = b1[i] - b0[i]; r[i] = a0[i] - b0[i]; }
@@ -531,7 +600,7 @@ static double seg_seg_dist(const double a0[3], const double a1[3], const double 
   if (t < 0) { t = 0; s = -c / a; s = s < 0 ? 0 : (s > 1 ? 1 : s); }
   else if (t > 1) { t = 1; s = (b - c) / a; s = s < 0 ? 0 : (s > 1 ? 1 : s); }
   double dd[3];
-  for (int i = 0; i < 3; i++) dd[i] = (a0[i] + s * d1[i]) - (b0[i] + t * d2[i]);
+  for (int i = 0; i < 3; i++) { pa[i] = a0[i] + s * d1[i]; pb[i] = b0[i] + t * d2[i]; dd[i] = pa[i] - pb[i]; }
   return sqrt(orc_dot3(dd, dd));
 }
 
@@ -584,9 +653,24 @@ static void collide(const orc_model* m, orc_data* d) {
           c0[i] = gpos[g2][i] - m->geom_size[g2][1] * gmat[g2][3 * i + 2];
           c1[i] = gpos[g2][i] + m->geom_size[g2][1] * gmat[g2][3 * i + 2];
         }
-        double gapd = seg_seg_dist(a0, a1, c0, c1) - m->geom_size[g1][0] - m->geom_size[g2][0];
+        double pa[3], pb[3];
+        double cd = seg_seg_dist(a0, a1, c0, c1, pa, pb);
+        double gapd = cd - m->geom_size[g1][0] - m->geom_size[g2][0];
         if (gapd < d->min_capsule_gap) d->min_capsule_gap = gapd;
-        continue;
+        if (gapd > margin || cd < 1e-12) continue;
+        /* mjc_CapsuleCapsule [EXT], non-parallel case: one contact at the closest points of the two axes; normal
+         * from geom1 to geom2, position midway between the two surfaces.  (Exactly parallel axes, where MuJoCo
+         * emits two contacts, are not modelled.) */
+        double nrm[3];
+        for (int i = 0; i < 3; i++) nrm[i] = (pb[i] - pa[i]) / cd;
+        cons[0].dist = gapd;
+        for (int i = 0; i < 3; i++) {
+          cons[0].pos[i] = pa[i] + nrm[i] * (m->geom_size[g1][0] + 0.5 * gapd);
+          cons[0].frame[i] = nrm[i]; cons[0].frame[3 + i] = 0;
+        }
+        make_frame(cons[0].frame);
+        cons[0].slot = 32 + (d->ncon & 31);
+        n = 1;
       }
       for (int c = 0; c < n && d->ncon < ORC_MAXCON; c++) {
         orc_contact* con = &d->contact[d->ncon++];
@@ -638,7 +722,7 @@ static void make_constraints(const orc_model* m, orc_data* d) {
   for (int j = 0; j < nv; j++) {
     if (!m->jnt_limited[j]) continue;
     for (int side = -1; side <= 1; side += 2) {
-      double dist = side * (m->jnt_range[j][side == -1 ? 0 : 1] - d->qpos[j]);
+      double dist = side * (m->jnt_range[j][side == -1 ? 0 : 1] - d->qpos[m->jnt_qadr[j]]);
       if (dist < 0 /* margin */) {
         memset(d->efc_J + n * nv, 0, sizeof(double) * nv);
         d->efc_J[n * nv + j] = -(double)side;
@@ -969,8 +1053,29 @@ void orc_step(const orc_model* m, orc_data* d, const double* ctrl) {
     memcpy(qacc, d->qacc, sizeof(double) * nv);
   for (int i = 0; i < nv; i++) {
     d->qvel[i] += h * qacc[i];
-    d->qpos[i] += h * d->qvel[i];
     d->qacc_warmstart[i] = d->qacc[i];
+  }
+  /* mj_integratePos [EXT]: scalar joints q += h v; a free joint's quaternion is rotated by h * (body-frame angular
+   * velocity) (mju_quatIntegrate: q <- q * [cos(a/2), sin(a/2) w/|w|], a = h |w|, then normalised) */
+  for (int i = 0; i < nv; i++) {
+    int qa = m->jnt_qadr[i];
+    if (m->jnt_type[i] == ORC_JNT_FREE_R) {
+      double w[3] = {d->qvel[i], d->qvel[i + 1], d->qvel[i + 2]};
+      double nw = sqrt(orc_dot3(w, w)), ang = h * nw;
+      if (nw > ORC_MINVAL) {
+        double sn = sin(0.5 * ang) / nw, cs = cos(0.5 * ang);
+        double r[4] = {cs, sn * w[0], sn * w[1], sn * w[2]};
+        double* q = d->qpos + qa;
+        double o[4] = {q[0] * r[0] - q[1] * r[1] - q[2] * r[2] - q[3] * r[3],
+                       q[0] * r[1] + q[1] * r[0] + q[2] * r[3] - q[3] * r[2],
+                       q[0] * r[2] - q[1] * r[3] + q[2] * r[0] + q[3] * r[1],
+                       q[0] * r[3] + q[1] * r[2] - q[2] * r[1] + q[3] * r[0]};
+        double no = sqrt(o[0] * o[0] + o[1] * o[1] + o[2] * o[2] + o[3] * o[3]);
+        for (int c = 0; c < 4; c++) q[c] = o[c] / no;
+      }
+      i += 2;
+    } else
+      d->qpos[qa] += h * d->qvel[i];
   }
   d->time += h;
 }
@@ -1034,4 +1139,36 @@ double orc_energy(const orc_model* m, const orc_data* d, double* kinetic, double
   if (kinetic) *kinetic = T;
   if (potential) *potential = U;
   return T + U;
+}
+
+/* ------------------------------------------------------------------ 3-D torque rollouts (see cassie_oracle.h) */
+long orc_rollout_tree(const orc_model* m, int n_envs, int n_steps, int hold, const double* actions,
+                      const double* qpos0, const double* qvel0, double z_done, const double* reset_qpos,
+                      const double* reset_qvel, double* out_qpos, double* out_qvel, int* out_resets, int n_threads) {
+  int nq = m->nq, nv = m->nv, nu = m->nu;
+  int nact = hold > 0 ? (n_steps + hold - 1) / hold : 1;
+  long total = 0;
+  (void)n_threads;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total) num_threads(n_threads > 0 ? n_threads : omp_get_max_threads())
+#endif
+  for (int e = 0; e < n_envs; e++) {
+    orc_data* d = orc_data_new(m);
+    orc_set_state(d, qpos0 + (size_t)e * nq, qvel0 + (size_t)e * nv);
+    int resets = 0;
+    for (int s = 0; s < n_steps; s++) {
+      const double* u = actions ? actions + ((size_t)e * nact + (hold > 0 ? s / hold : 0)) * nu : NULL;
+      orc_step(m, d, u);
+      total++;
+      if (z_done > 0 && hold > 0 && (s + 1) % hold == 0 && (d->qpos[2] < z_done || !(d->qpos[2] == d->qpos[2]))) {
+        orc_set_state(d, reset_qpos, reset_qvel);
+        memset(d->qacc_warmstart, 0, sizeof(d->qacc_warmstart));
+        resets++;
+      }
+    }
+    orc_get_state(d, out_qpos + (size_t)e * nq, out_qvel + (size_t)e * nv);
+    if (out_resets) out_resets[e] = resets;
+    orc_data_free(d);
+  }
+  return total;
 }

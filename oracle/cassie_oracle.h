@@ -31,16 +31,19 @@ extern "C" {
 #endif
 
 #define ORC_NB 24
-#define ORC_NV 16
+#define ORC_NV 24
+#define ORC_NQ (ORC_NV + 4)
 #define ORC_NG 16
-#define ORC_NS 8
+#define ORC_NS 12
 #define ORC_NEQ 4
-#define ORC_NU 8
-#define ORC_MAXCON 24
-#define ORC_MAXEFC 96
+#define ORC_NU 12
+#define ORC_MAXCON 32
+#define ORC_MAXEFC 128
 
 enum { ORC_GEOM_PLANE = 0, ORC_GEOM_SPHERE = 2, ORC_GEOM_CAPSULE = 3 };
-enum { ORC_JNT_SLIDE = 2, ORC_JNT_HINGE = 3 };
+/* ORC_JNT_FREE (cassie3d_stiff.xml:60) expands into six dofs: three world-axis translations (FREE_T) and three
+ * rotations about the body's own axes (FREE_R); its seven qpos entries are position + unit quaternion (w x y z) */
+enum { ORC_JNT_FREE = 0, ORC_JNT_SLIDE = 2, ORC_JNT_HINGE = 3, ORC_JNT_FREE_T = 10, ORC_JNT_FREE_R = 11 };
 enum { ORC_EFC_EQ = 0, ORC_EFC_LIMIT = 1, ORC_EFC_CONTACT = 2 };
 
 typedef struct orc_model orc_model;
@@ -72,6 +75,7 @@ int orc_compile(orc_model* m);
 orc_model* orc_model_rbdl_variant(const orc_model* m);
 
 int orc_nv(const orc_model* m);
+int orc_nq(const orc_model* m);
 int orc_nbody(const orc_model* m);
 double orc_total_mass(const orc_model* m);
 void orc_get_consts(const orc_model* m, double* body_invweight0 /*nbody*2*/,
@@ -156,6 +160,15 @@ void orc_cassie_osc_last(const orc_cassie* c, double x[39], double* obj, int* it
 long orc_rollout(const orc_model* phys, const orc_model* rbdl, int n_envs, int n_steps, int mode,
                  int hold, const double* actions, int adim, const double* phase,
                  const double* init_state26, double* out_state, int n_threads);
+/* 3-D torque rollouts (BASELINE configs[3], cassie3d_stiff.xml: no reference library exists for 3-D):
+ * every env starts at (qpos0[nq], qvel0[nv]) (per env), actions [n_envs][n_steps/hold][nu] held `hold` steps; when
+ * z_done > 0 an env whose pelvis height qpos[2] is below z_done after a held-action block is reset to
+ * (reset_qpos, reset_qvel) with a zero warm start (the rule borrowed from cassie_stand2d.py:131-133).
+ * out_qpos [n_envs][nq], out_qvel [n_envs][nv], out_resets [n_envs] (may be NULL).  returns total sim steps */
+long orc_rollout_tree(const orc_model* m, int n_envs, int n_steps, int hold, const double* actions,
+                      const double* qpos0, const double* qvel0, double z_done, const double* reset_qpos,
+                      const double* reset_qvel, double* out_qpos, double* out_qvel, int* out_resets, int n_threads);
+
 /* persistent env pool (bench.py --impl reference): envs, QP hot start and squat clocks survive across calls */
 typedef struct orc_pool orc_pool;
 orc_pool* orc_pool_new(const orc_model* phys, const orc_model* rbdl, int n_envs);

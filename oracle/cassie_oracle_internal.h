@@ -10,11 +10,11 @@
 #define ORC_MINVAL 1e-15
 
 struct orc_model {
-  int nbody, nv, ngeom, nsite, neq, nu;
+  int nbody, nv, nq, ngeom, nsite, neq, nu;
   int body_parent[ORC_NB], body_jntadr[ORC_NB], body_jntnum[ORC_NB];
   double body_pos[ORC_NB][3], body_mat[ORC_NB][9], body_ipos[ORC_NB][3], body_mass[ORC_NB];
   double body_inertia[ORC_NB][9];
-  int jnt_body[ORC_NV], jnt_type[ORC_NV], jnt_limited[ORC_NV];
+  int jnt_body[ORC_NV], jnt_type[ORC_NV], jnt_limited[ORC_NV], jnt_qadr[ORC_NV];
   double jnt_axis[ORC_NV][3], jnt_pos[ORC_NV][3], jnt_ref[ORC_NV], jnt_range[ORC_NV][2];
   double jnt_damping[ORC_NV], jnt_armature[ORC_NV], jnt_solref[ORC_NV][2], jnt_solimp[ORC_NV][5];
   int geom_body[ORC_NG], geom_type[ORC_NG], geom_contype[ORC_NG], geom_conaffinity[ORC_NG], geom_condim[ORC_NG];
@@ -30,11 +30,11 @@ struct orc_model {
   int iterations;
   /* compiled */
   unsigned char anc[ORC_NB][ORC_NV]; /* dof j moves body b */
-  double qpos0[ORC_NV], body_invweight0[ORC_NB][2], dof_invweight0[ORC_NV], meaninertia;
+  double qpos0[ORC_NQ], body_invweight0[ORC_NB][2], dof_invweight0[ORC_NV], meaninertia;
 };
 
 struct orc_kin {
-  double q[ORC_NV], qd[ORC_NV];
+  double q[ORC_NQ], qd[ORC_NV];
   double xpos[ORC_NB][3], xmat[ORC_NB][9], xipos[ORC_NB][3], Iw[ORC_NB][9];
   double S[ORC_NV][6], V[ORC_NB][6], A[ORC_NB][6];
 };
@@ -45,8 +45,8 @@ typedef struct {
 } orc_contact;
 
 struct orc_data {
-  int nv;
-  double qpos[ORC_NV], qvel[ORC_NV], qacc_warmstart[ORC_NV], time;
+  int nv, nq;
+  double qpos[ORC_NQ], qvel[ORC_NV], qacc_warmstart[ORC_NV], time;
   double ctrl[ORC_NU];
   orc_kin kin;
   double M[ORC_NV * ORC_NV], L[ORC_NV * ORC_NV];

@@ -21,7 +21,7 @@ import xml.etree.ElementTree as ET
 import numpy as np
 
 GEOM_PLANE, GEOM_SPHERE, GEOM_CAPSULE = 0, 2, 3
-JNT_SLIDE, JNT_HINGE = 2, 3
+JNT_FREE, JNT_SLIDE, JNT_HINGE = 0, 2, 3
 
 
 def _vec(s, n=None):
@@ -148,8 +148,10 @@ def read_mjcf(path):
                 limited = attr(j, "limited", "false") == "true"
                 rng = _vec(attr(j, "range", "0 0"), 2)
                 ref = float(attr(j, "ref", "0"))
+                if jt not in ("hinge", "slide", "free"):
+                    raise ValueError("unsupported joint type " + jt)
                 joints.append(dict(
-                    name=j.get("name"), body=bid, type=JNT_HINGE if is_hinge else JNT_SLIDE,
+                    name=j.get("name"), body=bid, type=JNT_FREE if jt == "free" else (JNT_HINGE if is_hinge else JNT_SLIDE),
                     axis=_vec(attr(j, "axis", "0 0 1"), 3), pos=_vec(attr(j, "pos", "0 0 0"), 3),
                     ref=ref * (ang if is_hinge else 1.0), limited=limited,
                     range=rng * (ang if is_hinge else 1.0),

@@ -79,7 +79,11 @@ def lib():
     L.orc_add_motor.argtypes = [vp, ct.c_int, ct.c_double, ct.c_int, c_dp]
     L.orc_set_option.argtypes = [vp, ct.c_double, ct.c_int, ct.c_double, ct.c_double, c_dp]
     L.orc_compile.argtypes = [vp]
-    for name in ("orc_nv", "orc_nbody"):
+    L.orc_add_joint.restype = ct.c_int
+    L.orc_rollout_tree.restype = ct.c_long
+    L.orc_rollout_tree.argtypes = [vp, ct.c_int, ct.c_int, ct.c_int, c_dp, c_dp, c_dp, ct.c_double, c_dp, c_dp,
+                                   c_dp, c_dp, c_ip, ct.c_int]
+    for name in ("orc_nv", "orc_nq", "orc_nbody"):
         getattr(L, name).argtypes = [vp]
     L.orc_get_consts.argtypes = [vp, c_dp, c_dp, c_dp, c_dp]
     L.orc_set_state.argtypes = [vp, c_dp, c_dp]
@@ -139,10 +143,12 @@ class Model:
         for b in sp["bodies"][1:]:
             L.orc_add_body(m, b["parent"], _dp(c(b["pos"])), _dp(c(b["mat"].reshape(-1))),
                            _dp(c(b["ipos"])), b["mass"], _dp(c(b["inertia"])))
+        self.joint_dof = []   # first dof of every MJCF joint (a free joint owns six)
         for j in sp["joints"]:
-            L.orc_add_joint(m, j["body"], j["type"], _dp(c(j["axis"])), _dp(c(j["pos"])), j["ref"],
-                            int(j["limited"]), _dp(c(j["range"])), j["damping"], j["armature"],
-                            _dp(c(j["solref"])), _dp(_solimp5(j["solimp"])))
+            self.joint_dof.append(L.orc_add_joint(
+                m, j["body"], j["type"], _dp(c(j["axis"])), _dp(c(j["pos"])), j["ref"],
+                int(j["limited"]), _dp(c(j["range"])), j["damping"], j["armature"],
+                _dp(c(j["solref"])), _dp(_solimp5(j["solimp"]))))
         for g in sp["geoms"]:
             L.orc_add_geom(m, g["body"], g["type"], _dp(c(g["pos"])), _dp(c(g["mat"].reshape(-1))),
                            _dp(c(g["size"])), g["contype"], g["conaffinity"], g["condim"],
@@ -154,7 +160,7 @@ class Model:
             L.orc_add_connect(m, e["body1"], e["body2"], _dp(c(e["anchor"])), _dp(c(e["solref"])),
                               _dp(_solimp5(e["solimp"])))
         for a in sp["actuators"]:
-            L.orc_add_motor(m, a["joint"], a["gear"], int(a["ctrllimited"]), _dp(c(a["ctrlrange"])))
+            L.orc_add_motor(m, self.joint_dof[a["joint"]], a["gear"], int(a["ctrllimited"]), _dp(c(a["ctrlrange"])))
         o = sp["option"]
         L.orc_set_option(m, o["timestep"], o["iterations"], o["tolerance"], o["impratio"],
                          _dp(c(o["gravity"])))
@@ -163,6 +169,7 @@ class Model:
         self.ptr = m
         self.rbdl_ptr = L.orc_model_rbdl_variant(m)
         self.nv = L.orc_nv(m)
+        self.nq = L.orc_nq(m)
         self.nbody = L.orc_nbody(m)
         self.nu = len(sp["actuators"])
 
@@ -191,7 +198,7 @@ class Data:
                             _dp(np.ascontiguousarray(qvel, np.float64)))
 
     def state(self):
-        q = np.zeros(self.m.nv); v = np.zeros(self.m.nv)
+        q = np.zeros(self.m.nq); v = np.zeros(self.m.nv)
         lib().orc_get_state(self.ptr, _dp(q), _dp(v))
         return q, v
 
@@ -393,6 +400,25 @@ def rollout(model, n_envs, n_steps, mode, actions=None, hold=1, phase=None, init
                           None if a is None else _dp(a), adim, None if ph is None else _dp(ph),
                           None if i26 is None else _dp(i26), _dp(out), n_threads)
     return n, out
+
+
+def model3d_path():
+    return os.path.join(_HERE, "..", "cassierl_b200", "model", "cassie3d_stiff.xml")
+
+
+def rollout_tree(model, qpos0, qvel0, n_steps, actions=None, hold=10, z_done=0.0, reset_qpos=None, reset_qvel=None,
+                 n_threads=0):
+    """3-D torque rollouts (orc_rollout_tree): qpos0 [n, nq], qvel0 [n, nv], actions [n, ceil(n_steps/hold), nu]."""
+    q0 = np.ascontiguousarray(qpos0, np.float64); v0 = np.ascontiguousarray(qvel0, np.float64)
+    n = q0.shape[0]
+    oq = np.zeros((n, model.nq)); ov = np.zeros((n, model.nv)); rs = np.zeros(n, np.int32)
+    a = None if actions is None else np.ascontiguousarray(actions, np.float64)
+    rq = None if reset_qpos is None else np.ascontiguousarray(reset_qpos, np.float64)
+    rv = None if reset_qvel is None else np.ascontiguousarray(reset_qvel, np.float64)
+    tot = lib().orc_rollout_tree(model.ptr, n, n_steps, hold, None if a is None else _dp(a), _dp(q0), _dp(v0),
+                                 float(z_done), None if rq is None else _dp(rq), None if rv is None else _dp(rv),
+                                 _dp(oq), _dp(ov), rs.ctypes.data_as(c_ip), n_threads)
+    return tot, oq, ov, rs
 
 
 class Pool:
