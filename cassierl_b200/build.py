@@ -19,11 +19,20 @@ LIB = os.path.join(HERE, "lib", "libcassie2d%s.so" % ("_" + VARIANT if VARIANT e
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr"]
-UNITS = ["kernels_f32.cu", "kernels_f64.cu", "rollout_f32.cu", "rollout_f64.cu", "cassie2d_api.cu", "mjcf_flatten.cpp"]
+UNITS = ["kernels_f32.cu", "kernels_f64.cu", "rollout_f32.cu", "rollout_f64.cu", "cassie2d_api.cu", "mjcf_flatten.cpp",
+         "tree_f32.cu", "tree_f64.cu", "cassie3d_api.cu"]
 
 
-def _deps():
-    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "cassie2d.h")]
+def _deps(unit=None):
+    """Files a translation unit is rebuilt for.  The four planar kernel units take minutes each and include neither the
+    3-D tree engine (tree_*, cassie3d_*) nor the host-side flattener, so edits there do not rebuild them."""
+    names = os.listdir(CSRC)
+    if unit and (unit.startswith("kernels_") or unit.startswith("rollout_")):
+        names = [f for f in names if f == unit or (f.endswith((".cuh", ".h")) and not f.startswith(("tree_", "cassie3d", "mjcf_flatten")))]
+    elif unit and (unit.startswith("tree_") or unit.startswith("cassie3d")):
+        names = [f for f in names if f == unit or f.startswith("tree_") and f.endswith((".cuh", ".h")) or f == "mjcf_flatten.h"]
+    inc = ("cassie3d.h",) if unit and (unit.startswith("tree_") or unit.startswith("cassie3d")) else ("cassie2d.h",)
+    return [os.path.join(CSRC, f) for f in names] + [os.path.join(HERE, "..", "include", h) for h in inc]
 
 
 def _stale(target, deps):
@@ -36,7 +45,7 @@ def _stale(target, deps):
 def _compile(unit, verbose):
     src = os.path.join(CSRC, unit)
     obj = os.path.join(OBJ, unit + ".o")
-    if not _stale(obj, _deps()):
+    if not _stale(obj, _deps(unit)):
         return obj
     # fp32 kernels: approximate (2 ulp) single-precision division / sqrt -- removes the IEEE slow-path
     # branches from the hot instruction stream (+8..30 %, profiles/r1_variants.txt); double is unaffected

@@ -1,6 +1,7 @@
 // Host-side MJCF reader + planar flattener (see mjcf_flatten.h).
 #include "mjcf_flatten.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -162,7 +163,7 @@ M3 axis_angle(V3 a, double ang) {
 
 struct Joint3 {
   std::string name;
-  bool hinge = true, limited = false;
+  bool hinge = true, limited = false, free = false;
   V3 axis{0, 0, 1}, pos;
   double ref = 0, lo = 0, hi = 0, damping = 0, armature = 0;
   double solref[2] = {0.02, 1}, solimp[5] = {0.9, 0.95, 0.001, 0.5, 2};
@@ -268,8 +269,9 @@ bool read_body(const XmlNode& e, int parent, const Defaults& df, double ang, Mod
       Joint3 j;
       j.name = k->get("name");
       const std::string type = dattr(*k, df.joint, "type", "hinge");
-      if (type != "hinge" && type != "slide") { *err = "unsupported joint type '" + type + "'"; return false; }
+      if (type != "hinge" && type != "slide" && type != "free") { *err = "unsupported joint type '" + type + "'"; return false; }
       j.hinge = type == "hinge";
+      j.free = type == "free";
       double a[3] = {0, 0, 1}, jp[3] = {0, 0, 0}, rg[2] = {0, 0};
       parse_doubles(dattr(*k, df.joint, "axis", "0 0 1"), 3, a);
       parse_doubles(dattr(*k, df.joint, "pos", "0 0 0"), 3, jp);
@@ -410,6 +412,8 @@ bool flatten(const Model3& M, const std::vector<double>& anchor_q, PlanarModel<d
   for (int b = 1; b < nb; b++)
     for (size_t j = 0; j < M.bodies[b].joints.size(); j++) jr.push_back({b, (int)j});
   if ((int)jr.size() != kNV) { *err = "expected 13 joints, found " + std::to_string(jr.size()); return false; }
+  for (auto& r : jr)
+    if (M.bodies[r.body].joints[r.idx].free) { *err = "free joint: not a planar model (use the tree engine)"; return false; }
   auto J = [&](int d) -> const Joint3& { return M.bodies[jr[d].body].joints[jr[d].idx]; };
   // link of each body: bodies without joints are welded to the parent's link
   std::vector<int> link_root(nb, 0);  // body that owns the link
@@ -659,6 +663,321 @@ bool flatten_mjcf_file(const std::string& path, FlatModels* out, std::string* er
   std::stringstream ss;
   ss << f.rdbuf();
   return flatten_mjcf_text(ss.str(), out, err);
+}
+
+// ------------------------------------------------------------------ 3-D tree flattener (cassie3d_stiff.xml)
+namespace {
+
+struct Rigid { V3 p; M3 R; };
+Rigid compose(const Rigid& a, const Rigid& b) { return {a.p + mul(a.R, b.p), mul(a.R, b.R)}; }
+
+M3 full_inertia(const double I[6]) {
+  M3 A;
+  A.m[0] = I[0]; A.m[4] = I[1]; A.m[8] = I[2];
+  A.m[1] = A.m[3] = I[3]; A.m[2] = A.m[6] = I[4]; A.m[5] = A.m[7] = I[5];
+  return A;
+}
+
+void mat_to_quat(const M3& R, double q[4]) {
+  const double* m = R.m;
+  const double tr = m[0] + m[4] + m[8];
+  if (tr > 0) {
+    const double s = std::sqrt(tr + 1.0) * 2;
+    q[0] = 0.25 * s; q[1] = (m[7] - m[5]) / s; q[2] = (m[2] - m[6]) / s; q[3] = (m[3] - m[1]) / s;
+  } else if (m[0] > m[4] && m[0] > m[8]) {
+    const double s = std::sqrt(1.0 + m[0] - m[4] - m[8]) * 2;
+    q[0] = (m[7] - m[5]) / s; q[1] = 0.25 * s; q[2] = (m[1] + m[3]) / s; q[3] = (m[2] + m[6]) / s;
+  } else if (m[4] > m[8]) {
+    const double s = std::sqrt(1.0 + m[4] - m[0] - m[8]) * 2;
+    q[0] = (m[2] - m[6]) / s; q[1] = (m[1] + m[3]) / s; q[2] = 0.25 * s; q[3] = (m[5] + m[7]) / s;
+  } else {
+    const double s = std::sqrt(1.0 + m[8] - m[0] - m[4]) * 2;
+    q[0] = (m[3] - m[1]) / s; q[1] = (m[2] + m[6]) / s; q[2] = (m[5] + m[7]) / s; q[3] = 0.25 * s;
+  }
+}
+
+// dense symmetric positive-definite inverse (Gauss-Jordan, n <= 24): init-time only
+bool spd_inverse(int n, const std::vector<double>& A, std::vector<double>* Ainv) {
+  std::vector<double> W(A);
+  Ainv->assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; i++) (*Ainv)[(size_t)i * n + i] = 1.0;
+  for (int k = 0; k < n; k++) {
+    const double piv = W[(size_t)k * n + k];
+    if (!(piv > 1e-14)) return false;
+    for (int j = 0; j < n; j++) { W[(size_t)k * n + j] /= piv; (*Ainv)[(size_t)k * n + j] /= piv; }
+    for (int i = 0; i < n; i++) {
+      if (i == k) continue;
+      const double f = W[(size_t)i * n + k];
+      if (f == 0) continue;
+      for (int j = 0; j < n; j++) { W[(size_t)i * n + j] -= f * W[(size_t)k * n + j]; (*Ainv)[(size_t)i * n + j] -= f * (*Ainv)[(size_t)k * n + j]; }
+    }
+  }
+  return true;
+}
+
+}  // namespace
+
+bool flatten_tree(const Model3& M, tree::TreeModel<double>* out, std::string* err) {
+  using namespace tree;
+  TreeModel<double>& m = *out;
+  std::memset(&m, 0, sizeof(m));
+  const int nb = (int)M.bodies.size();
+  // ---- links: one per jointed body; the free body first
+  int base = -1;
+  for (int b = 1; b < nb; b++)
+    for (auto& j : M.bodies[b].joints)
+      if (j.free) {
+        if (base >= 0 || M.bodies[b].joints.size() != 1 || M.bodies[b].parent != 0) { *err = "expected exactly one free joint, alone on a child of the world"; return false; }
+        base = b;
+      }
+  if (base < 0) { *err = "no free joint: not a floating-base model"; return false; }
+  std::vector<int> owner(nb, -1), depth(nb, 0);   // body that owns the link a body belongs to; link depth
+  std::vector<int> link_bodies;
+  for (int b = 1; b < nb; b++) {
+    const Body3& B = M.bodies[b];
+    if (!B.joints.empty()) {
+      if (b != base && (B.joints.size() != 1 || !B.joints[0].hinge)) { *err = "body " + B.name + ": expected one hinge per moving body"; return false; }
+      owner[b] = b;
+      depth[b] = B.parent == 0 ? 0 : depth[owner[B.parent]] + 1;
+      if (b != base && B.parent == 0) { *err = "only the free body may hang on the world"; return false; }
+      link_bodies.push_back(b);
+    } else {
+      if (B.parent == 0) { *err = "static bodies are not supported"; return false; }
+      owner[b] = owner[B.parent];
+    }
+  }
+  std::stable_sort(link_bodies.begin(), link_bodies.end(), [&](int a, int b) { return depth[a] < depth[b]; });
+  const int nl = (int)link_bodies.size();
+  if (nl > kMaxLinks || 5 + nl > kMaxDof) { *err = "too many links"; return false; }
+  std::vector<int> link_of(nb, -1);
+  for (int l = 0; l < nl; l++) link_of[link_bodies[l]] = l;
+  for (int b = 1; b < nb; b++) link_of[b] = link_of[owner[b]];
+  m.nl = nl; m.nv = 5 + nl; m.nq = 6 + nl;
+  // ---- rigid placement of every body in its link frame
+  std::vector<Rigid> in_link(nb);
+  for (int b = 1; b < nb; b++) {
+    const Body3& B = M.bodies[b];
+    if (owner[b] == b) in_link[b] = Rigid{V3{}, M3{}};
+    else in_link[b] = compose(in_link[B.parent], Rigid{B.pos, B.mat});
+  }
+  int nlev = 0;
+  for (int l = 0; l < nl; l++) {
+    const int b = link_bodies[l];
+    const Body3& B = M.bodies[b];
+    const int dl = depth[b];
+    if (dl + 1 > kMaxLevels) { *err = "tree too deep"; return false; }
+    if (dl + 1 > nlev) nlev = dl + 1;
+    m.level_off[dl + 1] = l + 1;
+    if (l == 0) {
+      m.parent[0] = -1;
+      m.anc[0] = 0x3fu;
+      m.qpos0[0] = B.pos.x; m.qpos0[1] = B.pos.y; m.qpos0[2] = B.pos.z;
+      mat_to_quat(B.mat, m.qpos0 + 3);
+      m.lmat[0][0] = m.lmat[0][4] = m.lmat[0][8] = 1;
+    } else {
+      const int pl = link_of[B.parent];
+      m.parent[l] = pl;
+      m.anc[l] = m.anc[pl] | (1u << (5 + l));
+      const Rigid X = compose(in_link[B.parent], Rigid{B.pos, B.mat});
+      m.lpos[l][0] = X.p.x; m.lpos[l][1] = X.p.y; m.lpos[l][2] = X.p.z;
+      for (int i = 0; i < 9; i++) m.lmat[l][i] = X.R.m[i];
+      const Joint3& J = B.joints[0];
+      m.axis[l][0] = J.axis.x; m.axis[l][1] = J.axis.y; m.axis[l][2] = J.axis.z;
+      m.jpos[l][0] = J.pos.x; m.jpos[l][1] = J.pos.y; m.jpos[l][2] = J.pos.z;
+      m.ref[l] = J.ref;
+      m.qpos0[6 + l] = J.ref;
+      const int d = 5 + l;
+      m.damping[d] = J.damping; m.armature[d] = J.armature; m.limited[d] = J.limited ? 1 : 0;
+      m.range[d][0] = J.lo; m.range[d][1] = J.hi;
+      for (int k = 0; k < 2; k++) m.lim_solref[d][k] = J.solref[k];
+      for (int k = 0; k < 5; k++) m.lim_solimp[d][k] = J.solimp[k];
+    }
+  }
+  {  // MuJoCo numbers dofs in file (depth-first) order; links are stored by depth
+    int next = 6;
+    for (int d = 0; d < 6; d++) m.user_dof[d] = d;
+    for (int b = 1; b < nb; b++)
+      if (owner[b] == b && b != base) m.user_dof[5 + link_of[b]] = next++;
+    for (int d = 0; d < m.nv; d++) m.dof_of_user[m.user_dof[d]] = d;
+  }
+  m.nlevels = nlev;
+  for (int k = 1; k <= nlev; k++) if (m.level_off[k] < m.level_off[k - 1]) m.level_off[k] = m.level_off[k - 1];
+  {
+    const Joint3& J = M.bodies[base].joints[0];
+    for (int d = 0; d < 6; d++) { m.damping[d] = J.damping; m.armature[d] = J.armature; }
+  }
+  {  // children lists
+    int k = 0;
+    for (int l = 0; l < nl; l++) {
+      m.child_off[l] = k;
+      for (int c = 0; c < nl; c++) if (m.parent[c] == l) m.child[k++] = c;
+    }
+    m.child_off[nl] = k;
+  }
+  // ---- welded bodies folded into their links
+  for (int l = 0; l < nl; l++) {
+    double mass = 0; V3 mc{};
+    for (int b = 1; b < nb; b++)
+      if (link_of[b] == l) { const V3 c = in_link[b].p + mul(in_link[b].R, M.bodies[b].ipos); mass += M.bodies[b].mass; mc = mc + M.bodies[b].mass * c; }
+    if (!(mass > 0)) { *err = "massless link"; return false; }
+    const V3 com = (1.0 / mass) * mc;
+    double I[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = 1; b < nb; b++) {
+      if (link_of[b] != l) continue;
+      const M3 Ib = mul(mul(in_link[b].R, full_inertia(M.bodies[b].I)), transpose(in_link[b].R));
+      const V3 c = in_link[b].p + mul(in_link[b].R, M.bodies[b].ipos);
+      const V3 d = c - com;
+      const double dv[3] = {d.x, d.y, d.z}, d2 = dot(d, d), mb = M.bodies[b].mass;
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) I[3 * i + j] += Ib.m[3 * i + j] + mb * ((i == j ? d2 : 0.0) - dv[i] * dv[j]);
+    }
+    m.mass[l] = mass;
+    m.com[l][0] = com.x; m.com[l][1] = com.y; m.com[l][2] = com.z;
+    m.inertia[l][0] = I[0]; m.inertia[l][1] = I[4]; m.inertia[l][2] = I[8];
+    m.inertia[l][3] = I[1]; m.inertia[l][4] = I[2]; m.inertia[l][5] = I[5];
+  }
+  // ---- options
+  m.timestep = M.timestep; m.tolerance = M.tolerance; m.impratio = M.impratio; m.iterations = M.iterations;
+  for (int i = 0; i < 3; i++) m.gravity[i] = M.gravity[i];
+  if (M.solver != "PGS" || M.cone != "elliptic") { *err = "only solver='PGS' with cone='elliptic' is implemented (cassie3d_stiff.xml:5)"; return false; }
+  // ---- qpos0 pose of every body (all hinges at ref: static composition), mass matrix, invweight0 (mj_setConst [EXT])
+  Pose3 P0;
+  fk3(M, std::vector<JointRef>(), std::vector<double>(), &P0);
+  const int nv = m.nv;
+  struct DofAxis { V3 w, p; bool rot; };
+  std::vector<DofAxis> dof(nv);
+  for (int k = 0; k < 3; k++) {
+    V3 e{k == 0 ? 1.0 : 0.0, k == 1 ? 1.0 : 0.0, k == 2 ? 1.0 : 0.0};
+    dof[k] = {e, V3{}, false};
+    dof[3 + k] = {mul(P0.xmat[base], e), P0.xpos[base], true};
+  }
+  for (int l = 1; l < nl; l++) {
+    const int b = link_bodies[l];
+    const Joint3& J = M.bodies[b].joints[0];
+    dof[5 + l] = {mul(P0.xmat[b], J.axis), P0.xpos[b] + mul(P0.xmat[b], J.pos), true};
+  }
+  auto moves = [&](int d, int b) { return (m.anc[link_of[b]] >> d) & 1u; };
+  auto jac = [&](int b, V3 P, std::vector<V3>* jp, std::vector<V3>* jr) {
+    jp->assign(nv, V3{}); jr->assign(nv, V3{});
+    for (int d = 0; d < nv; d++) {
+      if (!moves(d, b)) continue;
+      if (dof[d].rot) { (*jr)[d] = dof[d].w; (*jp)[d] = cross(dof[d].w, P - dof[d].p); }
+      else (*jp)[d] = dof[d].w;
+    }
+  };
+  std::vector<double> Mq((size_t)nv * nv, 0.0), Minv;
+  std::vector<V3> jp, jr;
+  for (int b = 1; b < nb; b++) {
+    const Body3& B = M.bodies[b];
+    if (B.mass <= 0) continue;
+    const V3 c = P0.xpos[b] + mul(P0.xmat[b], B.ipos);
+    const M3 Iw = mul(mul(P0.xmat[b], full_inertia(B.I)), transpose(P0.xmat[b]));
+    jac(b, c, &jp, &jr);
+    for (int i = 0; i < nv; i++) {
+      if (!moves(i, b)) continue;
+      const V3 Ir = mul(Iw, jr[i]);
+      for (int j = 0; j < nv; j++)
+        if (moves(j, b)) Mq[(size_t)i * nv + j] += B.mass * dot(jp[i], jp[j]) + dot(Ir, jr[j]);
+    }
+  }
+  double tr = 0;
+  for (int d = 0; d < nv; d++) { Mq[(size_t)d * nv + d] += m.armature[d]; tr += Mq[(size_t)d * nv + d]; }
+  m.meaninertia = tr / nv;
+  if (!spd_inverse(nv, Mq, &Minv)) { *err = "mass matrix at qpos0 is not positive definite"; return false; }
+  for (int d = 0; d < nv; d++) m.dof_invweight[d] = Minv[(size_t)d * nv + d];
+  std::vector<double> biw(nb, 0.0);
+  for (int b = 1; b < nb; b++) {
+    const V3 c = P0.xpos[b] + mul(P0.xmat[b], M.bodies[b].ipos);
+    jac(b, c, &jp, &jr);
+    double st = 0;
+    for (int r = 0; r < 3; r++)
+      for (int i = 0; i < nv; i++)
+        for (int j = 0; j < nv; j++) {
+          const double a = r == 0 ? jp[i].x : (r == 1 ? jp[i].y : jp[i].z), bb = r == 0 ? jp[j].x : (r == 1 ? jp[j].y : jp[j].z);
+          st += a * Minv[(size_t)i * nv + j] * bb;
+        }
+    biw[b] = std::max(st / 3, 1e-15);
+  }
+  // ---- geoms and collision pairs (mj_collision order: world geoms first, then bodies in tree order)
+  struct GRef { int body; const Geom3* g; int idx; };
+  std::vector<GRef> all;
+  for (int b = 0; b < nb; b++)
+    for (auto& g : M.bodies[b].geoms) all.push_back({b, &g, -1});
+  int ng = 0;
+  for (auto& r : all) {
+    if (r.body == 0) {
+      if (r.g->type != kPlane || m.has_plane) { *err = "the world may carry one plane only"; return false; }
+      m.has_plane = 1;
+      m.plane_pos[0] = r.g->pos.x; m.plane_pos[1] = r.g->pos.y; m.plane_pos[2] = r.g->pos.z;
+      m.plane_n[2] = 1.0;
+      continue;
+    }
+    if (ng >= kMaxGeoms) { *err = "too many collision geoms"; return false; }
+    const Rigid& X = in_link[r.body];
+    auto put = [&](double* d, V3 v) { const V3 w = X.p + mul(X.R, v); d[0] = w.x; d[1] = w.y; d[2] = w.z; };
+    m.g_link[ng] = link_of[r.body]; m.g_type[ng] = r.g->type; m.g_radius[ng] = r.g->radius;
+    if (r.g->type == kSphere) put(m.g_p0[ng], r.g->pos);
+    else if (r.g->type == kCapsule) { put(m.g_p0[ng], r.g->to); put(m.g_p1[ng], r.g->from); }
+    else { *err = "unsupported geom on a moving body"; return false; }
+    r.idx = ng++;
+  }
+  m.ng = ng;
+  int np = 0;
+  for (size_t i = 0; i < all.size(); i++)
+    for (size_t j = i + 1; j < all.size(); j++) {
+      const Geom3 &a = *all[i].g, &b = *all[j].g;
+      if (!((a.contype & b.conaffinity) || (b.contype & a.conaffinity))) continue;
+      if (all[i].body == all[j].body) continue;
+      const bool plane = all[i].body == 0;
+      if (!plane && !(a.type == kCapsule && b.type == kCapsule)) { *err = "only plane-sphere, plane-capsule and capsule-capsule pairs are implemented"; return false; }
+      if (!plane && link_of[all[i].body] == link_of[all[j].body]) continue;   // welded into one link: no relative motion
+      if (np >= kMaxPairs) { *err = "too many collision pairs"; return false; }
+      m.pair_a[np] = plane ? -1 : all[i].idx; m.pair_b[np] = all[j].idx;
+      m.pair_condim[np] = std::max(a.condim, b.condim);
+      if (m.pair_condim[np] != 3 && m.pair_condim[np] != 1) { *err = "only condim 1 and condim 3 contacts are implemented"; return false; }
+      for (int k = 0; k < 3; k++) m.pair_friction[np][k] = std::max(a.friction[k], b.friction[k]);
+      for (int k = 0; k < 2; k++) m.pair_solref[np][k] = 0.5 * (a.solref[k] + b.solref[k]);
+      for (int k = 0; k < 5; k++) m.pair_solimp[np][k] = 0.5 * (a.solimp[k] + b.solimp[k]);
+      m.pair_invweight[np] = biw[all[i].body] + biw[all[j].body];
+      np++;
+    }
+  m.npair = np;
+  // ---- connects: anchor2 = anchor1 seen from body2 at qpos0 (mjCModel compile [EXT]); both re-expressed in the link frames
+  if ((int)M.connects.size() > kMaxEq) { *err = "too many connects"; return false; }
+  m.neq = (int)M.connects.size();
+  for (int e = 0; e < m.neq; e++) {
+    const Connect3& C = M.connects[e];
+    const V3 Pw = P0.xpos[C.b1] + mul(P0.xmat[C.b1], C.anchor);
+    const V3 a2 = tmul(P0.xmat[C.b2], Pw - P0.xpos[C.b2]);
+    const V3 l1 = in_link[C.b1].p + mul(in_link[C.b1].R, C.anchor), l2 = in_link[C.b2].p + mul(in_link[C.b2].R, a2);
+    m.eq_l1[e] = link_of[C.b1]; m.eq_l2[e] = link_of[C.b2];
+    m.eq_a1[e][0] = l1.x; m.eq_a1[e][1] = l1.y; m.eq_a1[e][2] = l1.z;
+    m.eq_a2[e][0] = l2.x; m.eq_a2[e][1] = l2.y; m.eq_a2[e][2] = l2.z;
+    for (int k = 0; k < 2; k++) m.eq_solref[e][k] = C.solref[k];
+    for (int k = 0; k < 5; k++) m.eq_solimp[e][k] = C.solimp[k];
+    m.eq_invweight[e] = biw[C.b1] + biw[C.b2];
+  }
+  // ---- motors
+  if ((int)M.motors.size() > kMaxAct) { *err = "too many motors"; return false; }
+  m.nu = (int)M.motors.size();
+  for (int a = 0; a < m.nu; a++) {
+    const Motor3& mo = M.motors[a];
+    int d = -1;
+    for (int l = 1; l < nl; l++) if (M.bodies[link_bodies[l]].joints[0].name == mo.joint) d = 5 + l;
+    if (d < 0) { *err = "motor on unknown joint '" + mo.joint + "'"; return false; }
+    m.act_dof[a] = d; m.act_gear[a] = mo.gear; m.act_limited[a] = mo.limited ? 1 : 0; m.act_lo[a] = mo.lo; m.act_hi[a] = mo.hi;
+  }
+  return true;
+}
+
+bool flatten_tree_file(const std::string& path, tree::TreeModel<double>* out, std::string* err) {
+  std::ifstream f(path);
+  if (!f) { *err = "cannot open model file '" + path + "'"; return false; }
+  std::stringstream ss;
+  ss << f.rdbuf();
+  Model3 M;
+  if (!read_model3(ss.str(), &M, err)) return false;
+  return flatten_tree(M, out, err);
 }
 
 namespace {

@@ -8,6 +8,7 @@
 #pragma once
 #include <string>
 #include "planar_model.h"
+#include "tree_model.h"
 
 namespace cassie {
 
@@ -20,6 +21,9 @@ struct FlatModels {
 // planar model, or violates an assumption of the planar engine.
 bool flatten_mjcf_file(const std::string& path, FlatModels* out, std::string* err);
 bool flatten_mjcf_text(const std::string& xml, FlatModels* out, std::string* err);
+
+// Free-base 3-D models (cassie3d_stiff.xml) -> TreeModel (tree_model.h).  Same error contract.
+bool flatten_tree_file(const std::string& path, tree::TreeModel<double>* out, std::string* err);
 
 template <typename T>
 PlanarModel<T> cast_model(const PlanarModel<double>& s);

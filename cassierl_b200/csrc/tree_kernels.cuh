@@ -1,0 +1,144 @@
+// CUDA kernels of the 3-D tree engine (tree_engine.cuh): one env per tile of LANES lanes, the env's whole scratch block in
+// shared memory, all substeps of a policy step fused in one launch, termination + auto-reset in the same kernel.
+// State in HBM is row-major per env ([n][nq], [n][nv]: a tile reads its env's row with consecutive lanes -> coalesced),
+// in MuJoCo's dof order (file order); the engine's depth order is internal (TreeModel::user_dof).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "tree_engine.cuh"
+
+namespace cassie {
+void count_launch();
+namespace tree {
+
+template <typename T>
+struct TreeBatchView {
+  int n;
+  T* qpos;        // [n][nq]
+  T* qvel;        // [n][nv]
+  T* warm;        // [n][nv]  qacc_warmstart
+  int32_t* stats; // [n][4]: constraint rows, contacts, PGS sweeps of the last step; contacts dropped (cumulative)
+  int32_t* resets; // [n] auto-resets so far
+};
+
+struct TreeStepArgs {
+  const void* action;   // real [n][nu], held for n_sub simulator steps; nullptr = zero controls
+  int n_sub;
+  double z_done;        // > 0: done when the base height qpos[2] < z_done (cassie_stand2d.py:131-133) or the state is not finite
+  int auto_reset;       // done envs are put back to the reset state (zero warm start) inside the kernel
+  uint8_t* done;        // [n] or nullptr
+  const void* reset_q;  // real [nq] device
+  const void* reset_qd; // real [nv] device
+};
+
+template <typename T, int LANES>
+__global__ void __launch_bounds__(128)
+k_tree_step(const TreeModel<T>* __restrict__ gm, const TreeBatchView<T> v, const T* __restrict__ action, int n_sub, T z_done,
+            int auto_reset, uint8_t* __restrict__ done, const T* __restrict__ reset_q, const T* __restrict__ reset_qd) {
+  __shared__ TreeModel<T> m;
+  extern __shared__ __align__(16) unsigned char tree_smem[];
+  {  // the model block, once per CTA
+    const int words = (int)(sizeof(TreeModel<T>) / 4);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(gm);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&m);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const Tile<LANES> tl = Tile<LANES>::make();
+  const int tile_in_block = (int)threadIdx.x / LANES, tiles_per_block = (int)blockDim.x / LANES;
+  const int e = (int)blockIdx.x * tiles_per_block + tile_in_block;
+  if (e >= v.n) return;                       // whole tiles leave together; no block-wide barrier follows
+  Scratch<T>& s = *reinterpret_cast<Scratch<T>*>(tree_smem + (size_t)tile_in_block * sizeof(Scratch<T>));
+  const int nq = m.nq, nv = m.nv, nu = m.nu;
+  const T* gq = v.qpos + (size_t)e * nq;
+  const T* gv = v.qvel + (size_t)e * nv;
+  const T* gw = v.warm + (size_t)e * nv;
+  for (int i = tl.lane; i < 7; i += LANES) s.q[i] = gq[i];
+  for (int d = 6 + tl.lane; d < nv; d += LANES) s.q[d + 1] = gq[m.user_dof[d] + 1];
+  for (int d = tl.lane; d < nv; d += LANES) { s.qd[d] = gv[m.user_dof[d]]; s.warm[d] = gw[m.user_dof[d]]; }
+  for (int a = tl.lane; a < nu; a += LANES) s.ctrl[a] = action ? action[(size_t)e * nu + a] : (T)0;
+  if (tl.lane == 0) s.n_dropped = 0;
+  tl.sync();
+  TreeStats st = {0, 0, 0, 0};
+  for (int k = 0; k < n_sub; k++) tree_step(tl, m, s, s.ctrl, &st);
+  // termination (every lane evaluates it on the shared state) and auto-reset
+  bool bad = false;
+  for (int i = 0; i < nq; i++) bad = bad || !isfinite(s.q[i]);
+  for (int i = 0; i < nv; i++) bad = bad || !isfinite(s.qd[i]);
+  const bool fell = z_done > 0 && s.q[2] < z_done;
+  const bool is_done = bad || fell;
+  tl.sync();
+  if (is_done && auto_reset) {
+    for (int i = tl.lane; i < 7; i += LANES) s.q[i] = reset_q[i];
+    for (int d = 6 + tl.lane; d < nv; d += LANES) s.q[d + 1] = reset_q[m.user_dof[d] + 1];
+    for (int d = tl.lane; d < nv; d += LANES) { s.qd[d] = reset_qd[m.user_dof[d]]; s.warm[d] = 0; }
+    tl.sync();
+  }
+  T* oq = v.qpos + (size_t)e * nq;
+  T* ov = v.qvel + (size_t)e * nv;
+  T* ow = v.warm + (size_t)e * nv;
+  for (int i = tl.lane; i < 7; i += LANES) oq[i] = s.q[i];
+  for (int d = 6 + tl.lane; d < nv; d += LANES) oq[m.user_dof[d] + 1] = s.q[d + 1];
+  for (int d = tl.lane; d < nv; d += LANES) { ov[m.user_dof[d]] = s.qd[d]; ow[m.user_dof[d]] = s.warm[d]; }
+  if (tl.lane == 0) {
+    if (done) done[e] = bad ? 2 : (fell ? 1 : 0);
+    if (n_sub > 0) {
+      v.stats[4 * e + 0] = st.nefc; v.stats[4 * e + 1] = st.ncon; v.stats[4 * e + 2] = st.sweeps;
+      v.stats[4 * e + 3] += st.dropped;
+    }
+    if (is_done && auto_reset) v.resets[e] += 1;
+  }
+}
+
+// qpos / qvel of selected envs <- one state (reset); warm start cleared
+template <typename T>
+__global__ void k_tree_set_all(TreeBatchView<T> v, int nq, int nv, const T* __restrict__ q, const T* __restrict__ qd,
+                               const uint8_t* __restrict__ mask) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= v.n || (mask && !mask[e])) return;
+  for (int i = 0; i < nq; i++) v.qpos[(size_t)e * nq + i] = q[i];
+  for (int i = 0; i < nv; i++) { v.qvel[(size_t)e * nv + i] = qd[i]; v.warm[(size_t)e * nv + i] = 0; }
+}
+
+template <typename T>
+struct TreeLaunch {
+  static cudaError_t step(const TreeModel<T>* dm, const TreeBatchView<T>& v, const TreeStepArgs& a, int lanes, cudaStream_t s);
+  static cudaError_t set_all(const TreeBatchView<T>& v, int nq, int nv, const T* q, const T* qd, const uint8_t* mask, cudaStream_t s);
+};
+
+template <typename T, int LANES>
+inline cudaError_t launch_tree_step(const TreeModel<T>* dm, const TreeBatchView<T>& v, const TreeStepArgs& a, cudaStream_t s) {
+  constexpr int block = 128, tiles = block / LANES;
+  const size_t dyn = (size_t)tiles * sizeof(Scratch<T>);
+  static bool once = [&] {
+    cudaFuncSetAttribute(k_tree_step<T, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaFuncSetAttribute(k_tree_step<T, LANES>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return true;
+  }();
+  (void)once;
+  const unsigned grid = (unsigned)((v.n + tiles - 1) / tiles);
+  k_tree_step<T, LANES><<<grid, block, dyn, s>>>(dm, v, (const T*)a.action, a.n_sub, (T)a.z_done, a.auto_reset, a.done,
+                                                   (const T*)a.reset_q, (const T*)a.reset_qd);
+  count_launch();
+  return cudaGetLastError();
+}
+
+#define CASSIE_TREE_INSTANTIATE(T)                                                                                         \
+  template <>                                                                                                              \
+  cudaError_t TreeLaunch<T>::step(const TreeModel<T>* dm, const TreeBatchView<T>& v, const TreeStepArgs& a, int lanes,     \
+                                  cudaStream_t s) {                                                                        \
+    if (lanes == 8) return launch_tree_step<T, 8>(dm, v, a, s);                                                            \
+    if (lanes == 16) return launch_tree_step<T, 16>(dm, v, a, s);                                                          \
+    if (lanes == 32) return launch_tree_step<T, 32>(dm, v, a, s);                                                          \
+    return cudaErrorInvalidValue;                                                                                          \
+  }                                                                                                                        \
+  template <>                                                                                                              \
+  cudaError_t TreeLaunch<T>::set_all(const TreeBatchView<T>& v, int nq, int nv, const T* q, const T* qd,                   \
+                                     const uint8_t* mask, cudaStream_t s) {                                                \
+    k_tree_set_all<T><<<(v.n + 127) / 128, 128, 0, s>>>(v, nq, nv, q, qd, mask);                                           \
+    count_launch();                                                                                                        \
+    return cudaGetLastError();                                                                                             \
+  }
+
+}  // namespace tree
+}  // namespace cassie

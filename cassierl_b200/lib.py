@@ -25,6 +25,12 @@ BATCH_SYMBOLS = ["CassieGetLastError", "Cassie2dBatchInit", "Cassie2dBatchDestro
                  "Cassie2dBatchSquat", "Cassie2dBatchRollout", "Cassie2dBatchDiscountedReturns", "Cassie2dBatchBaselineMoments", "Cassie2dBatchAdvantages", "Cassie2dBatchStepHost", "Cassie2dBatchEnvStepHost", "Cassie2dBatchSquatHost",
                  "Cassie2dBatchGetStats", "Cassie2dBatchGetEpisodeLengths", "Cassie2dBatchSetWarmStart", "Cassie2dBatchGetWarmStart", "Cassie2dBatchSync", "CassieMeasureFp32Peak", "CassieKernelLaunchCount"]
 
+# every symbol include/cassie3d.h declares
+BATCH3D_SYMBOLS = ["Cassie3dGetLastError", "Cassie3dBatchCreate", "Cassie3dBatchDestroy", "Cassie3dBatchSizes",
+                   "Cassie3dBatchSetLanes", "Cassie3dBatchSetResetState", "Cassie3dBatchGetResetState", "Cassie3dBatchResetAll",
+                   "Cassie3dBatchSetState", "Cassie3dBatchGetState", "Cassie3dBatchGetWarmStart", "Cassie3dBatchSetWarmStart",
+                   "Cassie3dBatchStep", "Cassie3dBatchStepHost", "Cassie3dBatchGetStats", "Cassie3dBatchGetResets"]
+
 _lib = None
 
 
@@ -87,6 +93,26 @@ def load():
     L.GetOperationalSpaceState.restype = None
     L.Display.argtypes = [vp, ct.c_bool]
     L.Display.restype = None
+    # 3-D batch ABI (include/cassie3d.h)
+    i32p, u8p = ct.POINTER(ct.c_int32), ct.POINTER(ct.c_uint8)
+    L.Cassie3dGetLastError.restype = ct.c_char_p
+    L.Cassie3dBatchCreate.restype = vp
+    L.Cassie3dBatchCreate.argtypes = [ct.c_char_p, ci, ci, ci]
+    L.Cassie3dBatchDestroy.restype = None
+    L.Cassie3dBatchDestroy.argtypes = [vp]
+    L.Cassie3dBatchSizes.argtypes = [vp, i32p]
+    L.Cassie3dBatchSetLanes.argtypes = [vp, ci]
+    L.Cassie3dBatchSetResetState.argtypes = [vp, ct.POINTER(cd), ct.POINTER(cd)]
+    L.Cassie3dBatchGetResetState.argtypes = [vp, ct.POINTER(cd), ct.POINTER(cd)]
+    L.Cassie3dBatchResetAll.argtypes = [vp, vp, vp]
+    L.Cassie3dBatchSetState.argtypes = [vp, vp, vp, vp]
+    L.Cassie3dBatchGetState.argtypes = [vp, vp, vp, vp]
+    L.Cassie3dBatchGetWarmStart.argtypes = [vp, vp, vp]
+    L.Cassie3dBatchSetWarmStart.argtypes = [vp, vp, vp]
+    L.Cassie3dBatchStep.argtypes = [vp, vp, ci, cd, ci, vp, vp]
+    L.Cassie3dBatchStepHost.argtypes = [vp, vp, ci, cd, ci, vp, vp, vp]
+    L.Cassie3dBatchGetStats.argtypes = [vp, vp, vp]
+    L.Cassie3dBatchGetResets.argtypes = [vp, vp, vp]
     _lib = L
     return L
 

@@ -105,6 +105,85 @@ def harness(oracle):
     return Harness(out, oracle.default_model_path())
 
 
+class TreeHarness:
+    """ctypes view of tests/host_harness/tree_harness.cpp: the 3-D tree engine as a one-lane tile on the CPU."""
+
+    def __init__(self, path, xml):
+        self.L = ct.CDLL(path)
+        self.L.th_error.restype = ct.c_char_p
+        assert self.L.th_load(xml.encode()) == 0, self.L.th_error()
+        sz = (ct.c_int * 10)()
+        self.L.th_sizes(sz)
+        (self.nl, self.nv, self.nq, self.nu, self.ng, self.npair, self.neq, self.nlevels, self.scratch32, self.scratch64) = list(sz)
+
+    p = staticmethod(Harness.p)
+
+    @staticmethod
+    def ip(a):
+        return a.ctypes.data_as(ct.POINTER(ct.c_int))
+
+    def consts(self):
+        diw = np.zeros(self.nv); mi = ct.c_double(); piw = np.zeros(self.npair); eiw = np.zeros(self.neq)
+        q0 = np.zeros(self.nq); lm = np.zeros(self.nl)
+        self.L.th_consts(self.p(diw), ct.byref(mi), self.p(piw), self.p(eiw), self.p(q0), self.p(lm))
+        return dict(dof_invweight0=diw, meaninertia=mi.value, pair_invweight=piw, eq_invweight=eiw, qpos0=q0, link_mass=lm)
+
+    def dynamics(self, q, qd):
+        M = np.zeros((self.nv, self.nv)); b = np.zeros(self.nv)
+        self.L.th_dynamics(self.p(np.ascontiguousarray(q, np.float64)), self.p(np.ascontiguousarray(qd, np.float64)), self.p(M), self.p(b))
+        return M, b
+
+    def rows(self, q, qd):
+        J = np.zeros((48, self.nv)); pos = np.zeros(48); R = np.zeros(48); aref = np.zeros(48)
+        tp = np.zeros(48, np.int32); idd = np.zeros(48, np.int32)
+        n = self.L.th_rows(self.p(np.ascontiguousarray(q, np.float64)), self.p(np.ascontiguousarray(qd, np.float64)), self.p(J),
+                           self.p(pos), self.p(R), self.p(aref), self.ip(tp), self.ip(idd))
+        return dict(J=J[:n], pos=pos[:n], R=R[:n], aref=aref[:n], type=tp[:n], id=idd[:n])
+
+    def step(self, q, qd, warm, u, f32=False, n=1):
+        """n steps in place on (q, qd, warm); returns stats (rows, contacts, sweeps, dropped)"""
+        st = np.zeros(4, np.int32)
+        fn = self.L.th_steps_f32 if f32 else self.L.th_steps_f64
+        fn(int(n), self.p(q), self.p(qd), self.p(warm), self.p(np.ascontiguousarray(u, np.float64)), self.ip(st))
+        return st
+
+    def count_ops(self, q, qd, warm, u):
+        out = np.zeros(6, np.int64)
+        self.L.th_count_ops(self.p(np.ascontiguousarray(q, np.float64)), self.p(np.ascontiguousarray(qd, np.float64)),
+                            self.p(np.ascontiguousarray(warm, np.float64)), self.p(np.ascontiguousarray(u, np.float64)),
+                            out.ctypes.data_as(ct.POINTER(ct.c_long)))
+        return out
+
+
+@pytest.fixture(scope="session")
+def omodel3d(oracle):
+    return oracle.Model(oracle.model3d_path())
+
+
+@pytest.fixture(scope="session")
+def tree_harness(oracle):
+    src = os.path.join(ROOT, "tests", "host_harness", "tree_harness.cpp")
+    csrc = os.path.join(ROOT, "cassierl_b200", "csrc")
+    out = os.path.join(ROOT, "tests", "_build", "libtree_harness.so")
+    deps = [src] + [os.path.join(csrc, f) for f in ("tree_engine.cuh", "tree_model.h", "mjcf_flatten.cpp", "mjcf_flatten.h")]
+    if _stale(out, deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out, src, os.path.join(csrc, "mjcf_flatten.cpp")])
+    return TreeHarness(out, oracle.model3d_path())
+
+
+LEG_POSE_3D = [0.0, 0.0, 0.68111815, -1.40730357, 1.62972042, -1.77611107, -0.61968407]
+TORQUE_HIGH_3D = np.array([4.5, 4.5, 12.2, 12.2, 0.9] * 2)
+
+
+def pose3d(z=0.945):
+    """standing pose of Cassie2d.cpp:56-58 on the 3-D joints (abduction = yaw = 0); the toes touch the floor at z = 0.935"""
+    q = np.zeros(21)
+    q[2] = z; q[3] = 1.0
+    q[7:14] = LEG_POSE_3D; q[14:21] = LEG_POSE_3D
+    return q
+
+
 QPOS_INIT_PY = np.array([0.0, 0.939, 0.0, 0.68111815, -1.40730357, 1.62972042, -1.77611107, -0.61968407,
                          0.68111815, -1.40730357, 1.62972042, -1.77611107, -0.61968407])
 QPOS_INIT_CTOR = np.array([0.0, 0.939, 0.0, 0.68111815, -1.40730357, 1.62972042, -1.77611107, -0.61968407,

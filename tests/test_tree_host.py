@@ -1,0 +1,205 @@
+"""3-D tree engine (cassierl_b200/csrc/tree_engine.cuh, model/cassie3d_stiff.xml) on the CPU: the device code compiled
+as a one-lane tile (tests/host_harness/tree_harness.cpp) against the fp64 oracle, plus the oracle's own free-joint
+identities.  BASELINE.json configs[3]; SURVEY 8(f) row 2.  The reference has no 3-D library and no simulator outputs for
+this model (parity unpinned, like the planar path): the oracle is pinned by physical identities only.
+
+Error metric: max(|dq|, |dqvel| / max(1, |qvel|_inf)) per step -- absolute for positions / quaternion, norm-wise relative
+for velocities.
+"""
+import ctypes as ct
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, TORQUE_HIGH_3D, pose3d
+
+
+def _err(q, v, qo, vo):
+    return max(np.abs(q - qo).max(), np.abs(v - vo).max() / max(1.0, np.abs(vo).max()))
+
+
+# ------------------------------------------------------------------ the oracle's free joint
+def test_oracle_3d_model_and_free_fall(oracle, omodel3d):
+    m = omodel3d
+    assert (m.nv, m.nq, m.nu, m.nbody) == (20, 21, 10, 22)
+    assert abs(m.total_mass() - 32.822) < 1e-9          # same robot as the planar file
+    d = oracle.Data(m)
+    q, v = d.state()
+    q[2] = 2.0
+    d.set_state(q, v); d.forward()
+    assert len(d.contacts()["dist"]) == 0
+    vec = d.vectors()
+    assert np.abs(vec["qacc"][:6] - [0, 0, -9.806, 0, 0, 0]).max() < 1e-9      # cassie3d_stiff.xml:5
+    assert abs(vec["qfrc_bias"][2] - m.total_mass() * 9.806) < 1e-9
+    M = d.M()
+    assert np.abs(M - M.T).max() < 1e-12 and np.linalg.eigvalsh(M).min() > 0
+
+
+def test_oracle_3d_tumbling_momentum(oracle, omodel3d):
+    """free flight with spin: the centre of mass follows the semi-implicit Euler parabola and the horizontal momentum
+    is conserved up to the first-order integration error (halving dt halves it: checked when the oracle was extended)"""
+    m = omodel3d
+    d = oracle.Data(m)
+    rng = np.random.default_rng(0)
+    q = d.state()[0]
+    q[3:7] = rng.normal(size=4); q[3:7] /= np.linalg.norm(q[3:7]); q[2] = 3.0
+    v = np.zeros(m.nv); v[3:6] = [1.0, -2.0, 0.5]; v[0:3] = [0.3, 0.2, 0.1]; v[6:] = rng.normal(size=14) * 0.5
+    d.set_state(q, v); d.forward()
+    mass, g, h, n = m.total_mass(), 9.806, 0.0005, 200
+    z0 = d.energy()[2] / (mass * g)
+    p0 = (d.M() @ v)[:3]
+    for _ in range(n):
+        d.step(np.zeros(m.nu))
+    d.forward()
+    z1 = d.energy()[2] / (mass * g)
+    p1 = (d.M() @ d.state()[1])[:3]
+    assert abs(z1 - (z0 + n * h * p0[2] / mass - g * h * h * n * (n + 1) / 2)) < 1e-4
+    assert np.abs(p1[:2] - p0[:2]).max() < 5e-3 and abs(p1[2] - (p0[2] - mass * g * n * h)) < 5e-3
+    assert abs(np.linalg.norm(d.state()[0][3:7]) - 1) < 1e-12
+
+
+# ------------------------------------------------------------------ flattener
+def test_tree_flatten_constants(oracle, omodel3d, tree_harness):
+    th, c = tree_harness, omodel3d.consts()
+    assert (th.nl, th.nv, th.nq, th.nu, th.neq) == (15, 20, 21, 10, 2)
+    assert th.ng == 9 and th.npair == 9 + 9          # sphere + 8 capsules on the floor, 3 x 3 leg-leg capsule pairs
+    k = th.consts()
+    assert abs(k["meaninertia"] - c["meaninertia"]) < 1e-12
+    assert np.abs(k["dof_invweight0"] - c["dof_invweight0"]).max() < 1e-10
+    assert abs(k["link_mass"].sum() - omodel3d.total_mass()) < 1e-12
+    assert np.abs(k["qpos0"] - oracle.Data(omodel3d).state()[0]).max() == 0
+    # connects: heel spring (welded into the tarsus link) vs achilles rod
+    biw = c["body_invweight0"][:, 0]
+    names = omodel3d.spec["body_names"]
+    for e, side in enumerate(("left", "right")):
+        assert abs(k["eq_invweight"][e] - biw[names[side + "_achilles_rod"]] - biw[names[side + "_heel_spring"]]) < 1e-10
+
+
+def test_tree_mass_matrix_and_bias(oracle, omodel3d, tree_harness):
+    """composite-rigid-body M and recursive Newton-Euler bias of the device code vs the oracle's Jacobian-sum M and
+    world-frame RNE, at random poses (random quaternion, all 20 velocities non-zero)"""
+    rng = np.random.default_rng(1)
+    d = oracle.Data(omodel3d)
+    for _ in range(5):
+        q = d.state()[0].copy()
+        q[0:3] = rng.normal(size=3); qu = rng.normal(size=4); q[3:7] = qu / np.linalg.norm(qu)
+        q[7:] = omodel3d.consts()["eq_anchor2"].sum() * 0 + rng.normal(size=14) * 0.3 + pose3d()[7:]
+        v = rng.normal(size=20)
+        d.set_state(q, v); d.forward()
+        M, b = tree_harness.dynamics(q, v)
+        assert np.abs(M - d.M()).max() < 1e-11
+        assert np.abs(b - d.vectors()["qfrc_bias"]).max() < 1e-9
+
+
+def test_tree_rows_match(oracle, omodel3d, tree_harness):
+    """constraint Jacobians, violations, regularisation and reference accelerations after a landing"""
+    d = oracle.Data(omodel3d)
+    d.set_state(pose3d(0.94), np.zeros(20))
+    rng = np.random.default_rng(2)
+    u = rng.uniform(-1, 1, 10) * TORQUE_HIGH_3D
+    for k in range(120):
+        d.step(u)
+    q, v = d.state()
+    d.forward()
+    e = d.efc()
+    r = tree_harness.rows(q, v)
+    assert r["J"].shape == e["J"].shape and r["J"].shape[0] >= 9
+    assert (r["type"] == e["type"]).all()
+    assert np.abs(r["J"] - e["J"]).max() < 1e-12 and np.abs(r["pos"] - e["pos"]).max() < 1e-12
+    assert np.abs(r["R"] / e["R"] - 1).max() < 1e-10 and np.abs(r["aref"] - e["aref"]).max() < 1e-7
+
+
+# ------------------------------------------------------------------ steps
+def _run(oracle, m, th, U, f32, teacher, q0, v0=None):
+    d = oracle.Data(m)
+    d.set_state(q0, np.zeros(20) if v0 is None else v0)
+    q, v, w = q0.copy(), np.zeros(20) if v0 is None else v0.copy(), np.zeros(20)
+    errs, mism, rows = [], [], []
+    for k in range(len(U)):
+        if teacher:
+            q, v = (x.copy() for x in d.state()); w = d.warmstart().copy()
+        st = th.step(q, v, w, U[k], f32=f32)
+        d.step(U[k])
+        qo, vo = d.state()
+        errs.append(_err(q, v, qo, vo))
+        mism.append(int(st[0]) != d.efc()["J"].shape[0])
+        rows.append(int(st[0]))
+    return np.array(errs), np.array(mism), np.array(rows)
+
+
+@pytest.mark.parametrize("stream", ["zero", "random"])
+def test_tree_fp64_trajectory(oracle, omodel3d, tree_harness, stream):
+    """400 free-running steps from just above the floor (landing, toe contacts, joint limits under random torques):
+    1e-9 bar of the north-star for the fp64 build, constraint row counts identical step for step"""
+    rng = np.random.default_rng(0)
+    U = np.zeros((400, 10)) if stream == "zero" else np.repeat(rng.uniform(-1, 1, (40, 10)) * TORQUE_HIGH_3D, 10, axis=0)
+    e, mism, rows = _run(oracle, omodel3d, tree_harness, U, False, False, pose3d())
+    assert e.max() < 1e-9, e.max()
+    assert not mism.any()
+    assert rows.max() >= (12 if stream == "zero" else 10)       # 6 connect rows + contacts (+ limits)
+
+
+def test_tree_fp64_tilted_fall_many_contacts(oracle, omodel3d, tree_harness):
+    """a robot dropped on its side: pelvis sphere, thigh / shin / tarsus capsules on the floor, limits, leg-leg checks"""
+    q0 = pose3d(0.4)
+    ang = 1.2
+    q0[3:7] = [np.cos(ang / 2), np.sin(ang / 2), 0, 0]          # rolled about x
+    e, mism, rows = _run(oracle, omodel3d, tree_harness, np.zeros((700, 10)), False, False, q0)
+    assert e.max() < 1e-8, e.max()
+    assert not mism.any()
+    assert rows.max() >= 18
+
+
+def test_tree_fp32_single_step(oracle, omodel3d, tree_harness):
+    """fp32 build, teacher-forced single steps along the random-torque trajectory.  Bar: 1e-5 (north-star) on steps whose
+    contact / limit set equals the oracle's; a contact whose distance is within fp32 rounding of zero may appear one step
+    early or late (a hard event: its first impulse is O(B * v * h)), those steps are counted and bounded separately."""
+    rng = np.random.default_rng(0)
+    U = np.repeat(rng.uniform(-1, 1, (40, 10)) * TORQUE_HIGH_3D, 10, axis=0)
+    e, mism, _ = _run(oracle, omodel3d, tree_harness, U, True, True, pose3d())
+    same = e[~mism]
+    assert np.median(same) < 5e-6, np.median(same)
+    assert np.quantile(same, 0.95) < 1e-5, np.quantile(same, 0.95)
+    assert same.max() < 5e-5, same.max()
+    assert mism.sum() <= 8, mism.sum()
+    assert e.max() < 2e-2
+
+
+def test_tree_op_count(oracle, omodel3d, tree_harness):
+    """the algorithmic FLOP count tools/bench3d.py quotes (standing robot, 18 rows, 50 sweeps)"""
+    d = oracle.Data(omodel3d)
+    d.set_state(pose3d(0.93), np.zeros(20))
+    for _ in range(50):
+        d.step(np.zeros(10))
+    q, v = d.state()
+    out = tree_harness.count_ops(q, v, d.warmstart(), np.zeros(10))
+    flops = int(out[:3].sum())
+    assert out[4] >= 12 and 1 <= out[5] <= 50
+    assert 5e4 < flops < 1e6, flops
+
+
+# ------------------------------------------------------------------ ABI
+def test_cassie3d_header_symbols_exported():
+    from cassierl_b200 import build, lib
+    path = build.build()
+    hdr = open(os.path.join(ROOT, "include", "cassie3d.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(Cassie3d[A-Za-z0-9_]*)\s*\(", hdr)))
+    L = ct.CDLL(path)
+    assert not [n for n in names if not hasattr(L, n)]
+    assert names == sorted(lib.BATCH3D_SYMBOLS)
+
+
+def test_cassie3d_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from cassierl_b200 import lib
+    L = lib.load()
+    assert not L.Cassie3dBatchCreate(None, 4, 0, 32)
+    assert b"no CUDA device" in L.Cassie3dGetLastError()
+    from cassierl_b200.envs3d import Cassie3dBatch
+    with pytest.raises(RuntimeError):
+        Cassie3dBatch(4)
