@@ -66,6 +66,8 @@ def parse():
     p.add_argument("--preadvance", type=int, default=1000,
                    help="simulator steps every env is advanced OUTSIDE the timed region (steady state, not the start-up transient)")
     p.add_argument("--ref-envs", type=int, default=1024, help="--impl reference: envs of the bounded CPU sample")
+    p.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                   help="weak: --envs per GPU (the driver's contract); strong: --envs in TOTAL, split evenly over the ranks")
     return p.parse_args()
 
 
@@ -294,6 +296,10 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=dev)
     L = lib.load()
     n, sub, wl = args.envs, args.substeps, args.workload
+    if args.scaling == "strong":
+        if n % world:
+            raise SystemExit("bench.py: --scaling strong needs --envs divisible by the number of ranks")
+        n = n // world
     dt_t = torch.float64 if args.precision == 64 else torch.float32
     rs = 8 if args.precision == 64 else 4
     gid0 = rank * n                                   # global env ids: results independent of the GPU count
@@ -452,7 +458,7 @@ def run_native(args):
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_launch, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_launch, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[wl], "workload_key": wl, "envs_per_gpu": n, "sim_steps_per_launch": sub,
                        "policy_steps_per_s": value / sub, "preadvance_sim_steps": n_pre * sub,

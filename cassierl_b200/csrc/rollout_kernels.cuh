@@ -12,6 +12,8 @@
 #pragma once
 #include "env_kernels.cuh"
 #include "rollout_args.h"
+#include <cstdlib>
+#include <cstring>
 
 namespace cassie {
 
@@ -47,9 +49,67 @@ __device__ inline void normal8(uint64_t seed, uint32_t env, uint32_t step, T out
   }
 }
 
+// ---- tensor-core variant of the policy forward (A/B of VERDICT r1 item 8; CASSIE_MLP=tc, fp32 builds, thread engine)
+// One warp = 32 envs = the M dimension: H[32 x 32] = X[32 x K] W[K x 32] as mma.sync m16n8k8 TF32 tiles, every product
+// split 3xTF32 (a_hi b_hi + a_lo b_hi + a_hi b_lo) so that the result keeps fp32 accuracy (the parity bar against the
+// PyTorch fp32 reference is 1e-5; plain TF32 gives 1e-3).  Activations stay feature-major in shared memory
+// ([feature][env], the layout the scalar path stages the observation in), two buffers in ping-pong.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// out[j][env] = act(sum_i xs[i][env] w[i * ldw + j] + bias[j]) for the warp's 32 envs; NT = n-tiles of 8 outputs
+template <int NT, bool TANH>
+__device__ __forceinline__ void warp_dense_tc(const float* xs, int ldx, int K, const float* w, int ldw, int N, const float* bias,
+                                              float* out, int ldo) {
+  const int lane = (int)(threadIdx.x & 31u), g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < 2; mt++) {
+    float acc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+      const int j0 = 8 * nt + 2 * t;
+      const float b0 = j0 < N ? bias[j0] : 0.0f, b1 = j0 + 1 < N ? bias[j0 + 1] : 0.0f;
+      acc[nt][0] = b0; acc[nt][1] = b1; acc[nt][2] = b0; acc[nt][3] = b1;
+    }
+    for (int kt = 0; 8 * kt < K; kt++) {
+      const int i0 = 8 * kt + t, i1 = i0 + 4, r0 = 16 * mt + g;
+      const float a0 = i0 < K ? xs[i0 * ldx + r0] : 0.0f, a1 = i0 < K ? xs[i0 * ldx + r0 + 8] : 0.0f;
+      const float a2 = i1 < K ? xs[i1 * ldx + r0] : 0.0f, a3 = i1 < K ? xs[i1 * ldx + r0 + 8] : 0.0f;
+      uint32_t ah[4], al[4];
+      split_tf32(a0, ah[0], al[0]); split_tf32(a1, ah[1], al[1]); split_tf32(a2, ah[2], al[2]); split_tf32(a3, ah[3], al[3]);
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) {
+        const int j = 8 * nt + g;
+        const float w0 = (i0 < K && j < N) ? w[i0 * ldw + j] : 0.0f, w1 = (i1 < K && j < N) ? w[i1 * ldw + j] : 0.0f;
+        uint32_t bh[2], bl[2];
+        split_tf32(w0, bh[0], bl[0]); split_tf32(w1, bh[1], bl[1]);
+        mma_tf32(acc[nt], al, bh);
+        mma_tf32(acc[nt], ah, bl);
+        mma_tf32(acc[nt], ah, bh);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+      const int j0 = 8 * nt + 2 * t, r0 = 16 * mt + g;
+      float c0 = acc[nt][0], c1 = acc[nt][1], c2 = acc[nt][2], c3 = acc[nt][3];
+      if (TANH) { c0 = tanhf(c0); c1 = tanhf(c1); c2 = tanhf(c2); c3 = tanhf(c3); }
+      if (j0 < N) { out[j0 * ldo + r0] = c0; out[j0 * ldo + r0 + 8] = c2; }
+      if (j0 + 1 < N) { out[(j0 + 1) * ldo + r0] = c1; out[(j0 + 1) * ldo + r0 + 8] = c3; }
+    }
+  }
+  __syncwarp();
+}
+
 template <typename T>
 struct RolloutDev {
-  int task, flags, n_sub, T_steps, max_path_length, normalize;
+  int task, flags, n_sub, T_steps, max_path_length, normalize, mlp_tc;
   uint64_t seed;
   uint32_t env0;       // global id of this batch's env 0
   const T* params;     // flat [W1(in x 32) | b1 | W2(32 x 32) | b2 | W3(32 x adim) | b3 | log_std(adim)]  (Lasagne order)
@@ -71,7 +131,8 @@ __global__ void __launch_bounds__(kBlock, CASSIE_MIN_BLOCKS) k_rollout(const __g
   T* sp = reinterpret_cast<T*>(smem_raw);
   const int n_params = odim * kHidden + kHidden + kHidden * kHidden + kHidden + kHidden * adim + adim + adim;
   for (int i = threadIdx.x; i < n_params; i += kBlock) sp[i] = a.params[i];
-  T* sobs = sp + n_params;  // [26][kBlock] per-thread observation staging
+  T* sobs = sp + n_params;  // [26][kBlock] per-thread observation staging (+ [32][kBlock] hidden buffer, tensor-core variant)
+  T* shid = sobs + 26 * kBlock;
   __syncthreads();
   const T* W1 = sp; const T* b1 = W1 + odim * kHidden; const T* W2 = b1 + kHidden; const T* b2 = W2 + kHidden * kHidden;
   const T* W3 = b2 + kHidden; const T* b3 = W3 + kHidden * adim; const T* lstd = b3 + adim;
@@ -109,7 +170,26 @@ __global__ void __launch_bounds__(kBlock, CASSIE_MIN_BLOCKS) k_rollout(const __g
       }
     }
     // ---- GaussianMLPPolicy forward: tanh hidden layers, linear mean head (trpo_cassie.py:21-27)
-    T h1[kHidden], h2[kHidden], mu[adim], act[7];
+    T mu[adim], act[7];
+    bool mlp_done = false;
+    if constexpr (sizeof(T) == 4) {
+      if (a.mlp_tc) {
+        // whole warps only (the host enables this variant when n % 32 == 0): 32 envs x 32 hidden units per warp
+        const int wb = (int)(threadIdx.x & ~31u);
+        float* xs = reinterpret_cast<float*>(sobs) + wb;
+        float* hs = reinterpret_cast<float*>(shid) + wb;
+        __syncwarp();
+        warp_dense_tc<4, true>(xs, kBlock, odim, (const float*)W1, kHidden, kHidden, (const float*)b1, hs, kBlock);
+        warp_dense_tc<4, true>(hs, kBlock, kHidden, (const float*)W2, kHidden, kHidden, (const float*)b2, xs, kBlock);
+        warp_dense_tc<1, false>(xs, kBlock, kHidden, (const float*)W3, adim, adim, (const float*)b3, hs, kBlock);
+#pragma unroll
+        for (int c = 0; c < adim; c++) mu[c] = (T)hs[c * kBlock + (threadIdx.x & 31u)];
+        __syncwarp();
+        mlp_done = true;
+      }
+    }
+    if (!mlp_done) {
+    T h1[kHidden], h2[kHidden];
 #pragma unroll
     for (int j = 0; j < kHidden; j++) h1[j] = b1[j];
     for (int i = 0; i < odim; i++) {
@@ -132,6 +212,7 @@ __global__ void __launch_bounds__(kBlock, CASSIE_MIN_BLOCKS) k_rollout(const __g
 #pragma unroll
       for (int i = 0; i < kHidden; i++) s += h2[i] * W3[i * adim + c];
       mu[c] = s;
+    }
     }
     // ---- a = mean + exp(log_std) * eps ; NormalizedEnv: lb + (a + 1) / 2 (ub - lb), clipped (trpo_cassie.py:13)
     T eps[8];
@@ -353,6 +434,7 @@ RolloutDev<T> make_rollout_dev(const RolloutArgs& a) {
   RolloutDev<T> d;
   d.task = a.task; d.flags = a.flags; d.n_sub = a.n_substeps; d.T_steps = a.T_steps; d.max_path_length = a.max_path_length;
   d.normalize = a.normalize; d.seed = a.seed; d.env0 = a.env0;
+  d.mlp_tc = 0;
   d.params = (const T*)a.params; d.obs = (T*)a.obs; d.act = (T*)a.act; d.mean = (T*)a.mean; d.rew = (T*)a.rew; d.done = a.done;
   for (int i = 0; i < 7; i++) { d.act_lo[i] = (T)a.act_lo[i]; d.act_hi[i] = (T)a.act_hi[i]; }
   const double qi[26] = {0.0, 0.939, 0.0, 0.0, 0.0, 0.0, 0.68111815, -1.40730357, 1.62972042, -1.77611107, -0.61968407,
@@ -367,12 +449,14 @@ cudaError_t thread_rollout(const ModelPair<T>& mp, const BatchView<T>& v, const 
   const RolloutDev<T> d = make_rollout_dev<T>(a);
   const int odim = a.task == kTaskStand ? 17 : 26, adim = action_dim(a.mode);
   const int n_params = odim * kHidden + kHidden + kHidden * kHidden + kHidden + kHidden * adim + adim + adim;
-  const size_t smem = sizeof(T) * (size_t)(n_params + 26 * kBlock);
+  RolloutDev<T> dd = d;
+  if (const char* e = getenv("CASSIE_MLP")) dd.mlp_tc = (strcmp(e, "tc") == 0 && sizeof(T) == 4 && v.n % 32 == 0) ? 1 : 0;
+  const size_t smem = sizeof(T) * (size_t)(n_params + (26 + 32) * kBlock);
   const unsigned g = grid_for(v.n, kBlock);
   switch (a.mode) {
-    case kModeTorque: k_rollout<T, kModeTorque><<<g, kBlock, smem, s>>>(mp, v, d); break;
-    case kModePd: k_rollout<T, kModePd><<<g, kBlock, smem, s>>>(mp, v, d); break;
-    case kModeOsc: k_rollout<T, kModeOsc><<<g, kBlock, smem, s>>>(mp, v, d); break;
+    case kModeTorque: k_rollout<T, kModeTorque><<<g, kBlock, smem, s>>>(mp, v, dd); break;
+    case kModePd: k_rollout<T, kModePd><<<g, kBlock, smem, s>>>(mp, v, dd); break;
+    case kModeOsc: k_rollout<T, kModeOsc><<<g, kBlock, smem, s>>>(mp, v, dd); break;
     default: return cudaErrorInvalidValue;
   }
   count_launch();

@@ -12,8 +12,8 @@
 //
 // Formulation (deliberately not the oracle's): spatial vectors [angular; linear] in world axes about the BASE position
 // (so fp32 never sees the distance walked), composite-rigid-body mass matrix, recursive Newton-Euler bias with the
-// children pulled level by level, dense Cholesky shared by all right-hand sides, A = J M^-1 J^T + R kept in shared
-// memory, and a "publish" Gauss-Seidel sweep: every row owns its residual, a new force is broadcast and folded into all
+// children pulled level by level, dense Cholesky M = L L^T, one forward substitution per constraint row
+// (Y = L^-1 J^T in place of J, A = Y^T Y + R packed in shared memory, qacc and J^T f recovered from Y f), and a "publish" Gauss-Seidel sweep: every row owns its residual, a new force is broadcast and folded into all
 // residuals with one FMA per row.
 #pragma once
 #include <math.h>
@@ -31,7 +31,8 @@ namespace cassie {
 namespace tree {
 
 constexpr int kLD = kMaxDof + 1;       // row stride of [row][dof] arrays: odd, so lanes walking rows hit distinct banks
-constexpr int kLA = kMaxRows + 1;
+constexpr int kPackedA = kMaxRows * (kMaxRows + 1) / 2;   // A = J M^-1 J^T + R: lower triangle, row-packed
+TREE_HD int tri(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
 
 // ---------------------------------------------------------------------------------------------- tile runtime
 template <int LANES>
@@ -81,7 +82,8 @@ struct Scratch {
   T c_dist[kMaxCon], c_pos[kMaxCon][3], c_frame[kMaxCon][9];
   // constraint rows
   int r_type[kMaxRows], r_id[kMaxRows], r_sub[kMaxRows];
-  T J[kMaxRows * kLD], MiJ[kMaxRows * kLD], Am[kMaxRows * kLA];
+  T J[kMaxRows * kLD];                 // constraint Jacobian, overwritten by Y = L^-1 J^T (row r = y_r^T) before the solve
+  T Am[kPackedA];
   T r_pos[kMaxRows], r_R[kMaxRows], r_aref[kMaxRows], r_b[kMaxRows], r_f[kMaxRows], r_acc[kMaxRows];
 };
 
@@ -306,6 +308,18 @@ TREE_FN void cholesky(const Tile<LANES>& tl, int n, Scratch<T>& s, const T* add,
   }
 }
 
+// x <- L^-T x for one vector in shared memory, cooperative
+template <int LANES, typename T>
+TREE_FN void backward_one(const Tile<LANES>& tl, int n, const Scratch<T>& s, T* x) {
+  for (int k = n - 1; k >= 0; k--) {
+    const T xk = x[k] * s.dinv[k];
+    tl.sync();
+    if (tl.lane == 0) x[k] = xk;
+    for (int j = tl.lane; j < k; j += LANES) x[j] -= s.L[k * kLD + j] * xk;
+    tl.sync();
+  }
+}
+
 // x <- (L L^T)^-1 x for one vector in shared memory, cooperative (column sweeps, one FMA per lane and step)
 template <int LANES, typename T>
 TREE_FN void solve_one(const Tile<LANES>& tl, int n, const Scratch<T>& s, T* x) {
@@ -316,26 +330,15 @@ TREE_FN void solve_one(const Tile<LANES>& tl, int n, const Scratch<T>& s, T* x) 
     for (int i = k + 1 + tl.lane; i < n; i += LANES) x[i] -= s.L[i * kLD + k] * xk;
     tl.sync();
   }
-  for (int k = n - 1; k >= 0; k--) {
-    const T xk = x[k] * s.dinv[k];
-    tl.sync();
-    if (tl.lane == 0) x[k] = xk;
-    for (int j = tl.lane; j < k; j += LANES) x[j] -= s.L[k * kLD + j] * xk;
-    tl.sync();
-  }
+  backward_one(tl, n, s, x);
 }
 
-// one lane, one right-hand side (rows of MiJ), serial
+// one lane, one right-hand side: x <- L^-1 x (forward substitution, serial)
 template <typename T>
-TREE_FN void solve_row(int n, const Scratch<T>& s, T* x) {
+TREE_FN void forward_row(int n, const Scratch<T>& s, T* x) {
   for (int i = 0; i < n; i++) {
     T v = x[i];
     for (int j = 0; j < i; j++) v -= s.L[i * kLD + j] * x[j];
-    x[i] = v * s.dinv[i];
-  }
-  for (int i = n - 1; i >= 0; i--) {
-    T v = x[i];
-    for (int j = i + 1; j < n; j++) v -= s.L[j * kLD + i] * x[j];
     x[i] = v * s.dinv[i];
   }
 }
@@ -570,25 +573,26 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
     tl.sync();
     return;
   }
-  // M^-1 J^T, one right-hand side per lane
+  // b = J qacc_smooth - aref, jar = J qacc_warmstart - aref (kept in r_pos, which make_rows is done with), then
+  // Y = L^-1 J^T in place of J, one right-hand side per lane
   for (int r = tl.lane; r < nefc; r += LANES) {
-    T* x = s.MiJ + r * kLD;
-    const T* Jr = s.J + r * kLD;
-    T bsum = 0;
-    for (int d = 0; d < nv; d++) { x[d] = Jr[d]; bsum += Jr[d] * s.qacc_s[d]; }
+    T* Jr = s.J + r * kLD;
+    T bsum = 0, wsum = 0;
+    for (int d = 0; d < nv; d++) { bsum += Jr[d] * s.qacc_s[d]; wsum += Jr[d] * s.warm[d]; }
     s.r_b[r] = bsum - s.r_aref[r];
-    solve_row(nv, s, x);
+    s.r_pos[r] = wsum - s.r_aref[r];
+    forward_row(nv, s, Jr);
   }
   tl.sync();
   for (int r = tl.lane; r < nefc; r += LANES) {
-    const T* Jr = s.J + r * kLD;
+    const T* Yr = s.J + r * kLD;
+    T* Ar = s.Am + r * (r + 1) / 2;
     for (int c = 0; c <= r; c++) {
-      const T* Mc = s.MiJ + c * kLD;
+      const T* Yc = s.J + c * kLD;
       T v = 0;
-      for (int d = 0; d < nv; d++) v += Jr[d] * Mc[d];
+      for (int d = 0; d < nv; d++) v += Yr[d] * Yc[d];
       if (c == r) v += s.r_R[r];
-      s.Am[r * kLA + c] = v;
-      s.Am[c * kLA + r] = v;
+      Ar[c] = v;
     }
   }
   tl.sync();
@@ -598,12 +602,7 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
     const int type = s.r_type[r];
     const int dim = type == kRowContact ? s.c_dim[s.r_id[r]] : 1;
     T jar[3];
-    for (int j = 0; j < dim; j++) {
-      const T* Jr = s.J + (r + j) * kLD;
-      T v = 0;
-      for (int d = 0; d < nv; d++) v += Jr[d] * s.warm[d];
-      jar[j] = v - s.r_aref[r + j];
-    }
+    for (int j = 0; j < dim; j++) jar[j] = s.r_pos[r + j];
     if (type == kRowEq) s.r_f[r] = -jar[0] / s.r_R[r];
     else if (dim == 1) s.r_f[r] = jar[0] < 0 ? -jar[0] / s.r_R[r] : (T)0;    // joint limit, frictionless contact
     else {
@@ -626,9 +625,8 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
   tl.sync();
   T cost = 0;
   for (int r = tl.lane; r < nefc; r += LANES) {
-    const T* Ar = s.Am + r * kLA;
     T v = 0;
-    for (int c = 0; c < nefc; c++) v += Ar[c] * s.r_f[c];
+    for (int c = 0; c < nefc; c++) v += s.Am[tri(r, c)] * s.r_f[c];
     s.r_acc[r] = v;
     cost += s.r_f[r] * ((T)0.5 * v + s.r_b[r]);
   }
@@ -653,7 +651,7 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
         res[j] = s.r_acc[i + j];
         old[j] = s.r_f[i + j];
         fn[j] = old[j];
-        for (int c = 0; c < dim; c++) At[3 * j + c] = s.Am[(i + j) * kLA + i + c];
+        for (int c = 0; c < dim; c++) At[3 * j + c] = s.Am[tri(i + j, i + c)];
       }
       if (dim == 1) {
         fn[0] -= res[0] / At[0];
@@ -708,7 +706,7 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
         for (int j = 0; j < dim; j++) s.r_f[i + j] = old[j] + delta[j];
       for (int r = tl.lane; r < nefc; r += LANES) {
         T a = s.r_acc[r];
-        for (int j = 0; j < dim; j++) a += s.Am[(i + j) * kLA + r] * delta[j];
+        for (int j = 0; j < dim; j++) a += s.Am[tri(i + j, r)] * delta[j];
         s.r_acc[r] = a;
       }
       tl.sync();
@@ -718,13 +716,21 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
     if (improvement * scale < m.tolerance) break;
   }
   if (tl.lane == 0) s.sweeps = iter;
-  // qfrc_constraint = J^T f ; qacc = qacc_smooth + M^-1 J^T f
+  // z = Y f ; qfrc_constraint = J^T f = L z ; qacc = qacc_smooth + M^-1 J^T f = qacc_smooth + L^-T z
   for (int d = tl.lane; d < nv; d += LANES) {
-    T a = 0, b = 0;
-    for (int r = 0; r < nefc; r++) { a += s.J[r * kLD + d] * s.r_f[r]; b += s.MiJ[r * kLD + d] * s.r_f[r]; }
-    s.qfc[d] = a;
-    s.qacc[d] = s.qacc_s[d] + b;
+    T a = 0;
+    for (int r = 0; r < nefc; r++) a += s.J[r * kLD + d] * s.r_f[r];
+    s.qacc[d] = a;
   }
+  tl.sync();
+  for (int i = tl.lane; i < nv; i += LANES) {
+    T a = 0;
+    for (int j = 0; j <= i; j++) a += s.L[i * kLD + j] * s.qacc[j];
+    s.qfc[i] = a;
+  }
+  tl.sync();
+  backward_one(tl, nv, s, s.qacc);
+  for (int d = tl.lane; d < nv; d += LANES) s.qacc[d] += s.qacc_s[d];
   tl.sync();
 }
 

@@ -61,6 +61,25 @@ def test_policy_forward_noise_and_action_map(R, mode, task):
     col.close(); col2.close()
 
 
+@pytest.mark.parametrize("task", ["stand", "imitate"])
+def test_policy_forward_tensor_core_variant(R, task, monkeypatch):
+    """CASSIE_MLP=tc: the 3xTF32 mma.sync forward pass of the thread-engine rollout kernel (PD action space) against
+    the same PyTorch fp32 reference and the same 1e-5 bar, and against the scalar kernel's means"""
+    n, T = 96, 6
+    pol = None
+    means = {}
+    for variant in ("scalar", "tc"):
+        monkeypatch.setenv("CASSIE_MLP", variant)
+        col = R.RolloutCollector(n, task=task, control_mode="PD", precision=32, seed=12345, first_global_env=1000)
+        pol = pol or R.GaussianMLPPolicy(col.obs_dim, col.act_dim, seed=3)
+        out = col.collect(pol, T)
+        ref = pol.mean(out["observations"].reshape(-1, col.obs_dim)).reshape(T, n, col.act_dim)
+        assert float((out["means"] - ref).abs().max() / ref.abs().max().clamp(min=1)) < 1e-5, variant
+        means[variant] = out["means"][0].clone()        # step 0: same observation in both runs
+        col.close()
+    assert float((means["tc"] - means["scalar"]).abs().max()) < 2e-6
+
+
 def test_rollout_transitions_match_env_step(R):
     """Replaying the recorded (normalised, clipped) actions through Cassie2dBatchEnv.step reproduces
     the rollout's observations, rewards and dones (fp64 build, 1e-9)."""

@@ -1,0 +1,151 @@
+"""GPU parity of the 3-D tree engine (BASELINE.json configs[3]: cassie3d_stiff.xml) through the C-ABI of
+include/cassie3d.h, against the fp64 oracle on the same initial states and torque sequences.  Every lane width of the
+step kernel (8, 16, 32 lanes per env) is checked.  Error metric as in tests/test_tree_host.py."""
+import numpy as np
+import pytest
+
+from conftest import TORQUE_HIGH_3D, pose3d
+
+pytestmark = pytest.mark.gpu
+
+
+def _starts(n, seed=0):
+    """standing poses just above the floor with perturbed joints, headings and small velocities"""
+    rng = np.random.default_rng(seed)
+    q = np.tile(pose3d(0.945), (n, 1))
+    q[:, 7:] += rng.normal(size=(n, 14)) * 0.03
+    yaw = rng.uniform(-np.pi, np.pi, n)
+    roll = rng.normal(size=n) * 0.05
+    for e in range(n):
+        a = np.array([np.cos(yaw[e] / 2), 0, 0, np.sin(yaw[e] / 2)]); b = np.array([np.cos(roll[e] / 2), np.sin(roll[e] / 2), 0, 0])
+        q[e, 3:7] = [a[0] * b[0], a[0] * b[1], a[3] * b[1], a[3] * b[0]]   # quaternion product yaw * roll
+        q[e, 3:7] /= np.linalg.norm(q[e, 3:7])
+    q[:, 0:2] = rng.normal(size=(n, 2)) * 3.0
+    v = rng.normal(size=(n, 20)) * 0.05
+    return q, v
+
+
+def _err(q, v, qo, vo):
+    return np.maximum(np.abs(q - qo).max(axis=1), np.abs(v - vo).max(axis=1) / np.maximum(1.0, np.abs(vo).max(axis=1)))
+
+
+@pytest.mark.parametrize("lanes", [8, 16, 32])
+def test_tree_fp64_rollout_vs_oracle(oracle, omodel3d, lanes):
+    """16 envs x 200 free-running steps, random torques held 10 steps (configs[3] actions): 1e-9 in the fp64 build"""
+    import torch
+    from cassierl_b200.envs3d import Cassie3dBatch
+    n, steps, hold = 16, 200, 10
+    q0, v0 = _starts(n)
+    rng = np.random.default_rng(1)
+    A = rng.uniform(-1, 1, (n, steps // hold, 10)) * TORQUE_HIGH_3D
+    b = Cassie3dBatch(n, precision=64, lanes=lanes)
+    assert (b.nq, b.nv, b.nu) == (21, 20, 10)
+    b.set_state(q0, v0)
+    for k in range(steps // hold):
+        b.step(torch.tensor(A[:, k]), n=hold)
+    q, v = (x.cpu().numpy() for x in b.state())
+    st = b.stats().cpu().numpy()
+    b.close()
+    _, qo, vo, _ = oracle.rollout_tree(omodel3d, q0, v0, steps, actions=A, hold=hold)
+    e = _err(q, v, qo, vo)
+    assert e.max() < 1e-9, e
+    assert st[:, 0].max() >= 12 and st[:, 3].sum() == 0
+
+
+def test_tree_fp64_fall_and_autoreset_bit_exact(oracle, omodel3d):
+    """robots pushed over: done flags (pelvis below 0.5 m) and the number of auto-resets are bit-exact against the
+    oracle's rollout with the same rule, final states agree to 1e-8 (resets included)"""
+    import torch
+    from cassierl_b200.envs3d import Cassie3dBatch
+    n, steps, hold = 24, 1200, 10
+    q0, v0 = _starts(n, seed=3)
+    v0[:, 3:6] += np.random.default_rng(4).normal(size=(n, 3)) * 1.5      # tumbling
+    b = Cassie3dBatch(n, precision=64)
+    rq, rv = b.reset_state()
+    b.set_state(q0, v0)
+    dones = np.zeros(n, np.int64)
+    for k in range(steps // hold):
+        d = b.step(None, n=hold, z_done=0.5, auto_reset=True)
+        dones += (d.cpu().numpy() != 0)
+    q, v = (x.cpu().numpy() for x in b.state())
+    resets = b.resets().cpu().numpy()
+    b.close()
+    _, qo, vo, ro = oracle.rollout_tree(omodel3d, q0, v0, steps, actions=None, hold=hold, z_done=0.5, reset_qpos=rq, reset_qvel=rv)
+    assert (resets == ro).all() and (dones == ro).all()
+    assert ro.sum() >= n // 2            # unactuated robots collapse: most envs fell at least once
+    assert _err(q, v, qo, vo).max() < 1e-8
+
+
+@pytest.mark.parametrize("lanes", [8, 32])
+def test_tree_fp32_single_step_vs_oracle(oracle, omodel3d, lanes):
+    """fp32 build, teacher-forced: every step starts from the oracle's state and warm start.  1e-5 on the steps whose
+    constraint-row count equals the oracle's; event mismatches (a contact within fp32 rounding of touching) are rare"""
+    import torch
+    from cassierl_b200.envs3d import Cassie3dBatch
+    n, steps = 32, 120
+    q0, v0 = _starts(n, seed=5)
+    rng = np.random.default_rng(6)
+    A = rng.uniform(-1, 1, (n, steps // 10, 10)) * TORQUE_HIGH_3D
+    datas = [oracle.Data(omodel3d) for _ in range(n)]
+    for e in range(n):
+        datas[e].set_state(q0[e], v0[e])
+    b = Cassie3dBatch(n, precision=32, lanes=lanes)
+    errs, same = [], []
+    for k in range(steps):
+        qs = np.stack([d.state()[0] for d in datas]); vs = np.stack([d.state()[1] for d in datas])
+        ws = np.stack([d.warmstart() for d in datas])
+        b.set_state(qs, vs); b.set_warm_start(ws)
+        b.step(torch.tensor(A[:, k // 10]), n=1)
+        q, v = (x.cpu().numpy().astype(np.float64) for x in b.state())
+        rows = b.stats().cpu().numpy()[:, 0]
+        for e in range(n):
+            datas[e].step(A[e, k // 10])
+        qo = np.stack([d.state()[0] for d in datas]); vo = np.stack([d.state()[1] for d in datas])
+        ro = np.array([d.efc()["J"].shape[0] for d in datas])
+        errs.append(_err(q, v, qo, vo)); same.append(rows == ro)
+    b.close()
+    errs, same = np.array(errs), np.array(same)
+    ok = errs[same]
+    assert np.median(ok) < 5e-6 and np.quantile(ok, 0.95) < 1e-5, (np.median(ok), np.quantile(ok, 0.95))
+    assert ok.max() < 1e-4, ok.max()
+    assert (~same).mean() < 0.02, (~same).mean()
+
+
+def test_tree_config4_shard_invariants():
+    """one GPU's shard of configs[3] (65536 envs over 8 GPUs = 8192 per GPU), fp32, random torques, auto-reset on fall:
+    states stay finite, quaternions unit, resets happen, no contact is dropped for capacity in the common case"""
+    import torch
+    from cassierl_b200.envs3d import Cassie3dBatch, TORQUE_HIGH_3D as HI
+    n = 8192
+    b = Cassie3dBatch(n, precision=32)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    hi = torch.tensor(HI, dtype=torch.float32, device="cuda")
+    fell = torch.zeros(n, dtype=torch.int64, device="cuda")
+    for k in range(60):
+        a = (torch.rand((n, 10), generator=g, device="cuda") * 2 - 1) * hi
+        d = b.step(a, n=10, z_done=0.5, auto_reset=True)
+        fell += (d != 0)
+    q, v = b.state()
+    st = b.stats()
+    assert torch.isfinite(q).all() and torch.isfinite(v).all()
+    assert (q[:, 3:7].norm(dim=1) - 1).abs().max() < 1e-5
+    assert (q[:, 2] > 0.3).all()                       # nobody is left lying on the floor
+    assert fell.sum() > n // 4 and (b.resets() == fell.to(torch.int32)).all()
+    assert (d != 2).all()                              # no env went non-finite
+    assert st[:, 3].sum().item() <= n // 100           # capacity drops are rare
+    b.close()
+
+
+def test_tree_step_host_matches_device():
+    import torch
+    from cassierl_b200.envs3d import Cassie3dBatch, TORQUE_HIGH_3D as HI
+    n = 64
+    a = (torch.rand((n, 10)) * 2 - 1) * torch.tensor(HI, dtype=torch.float32)
+    b1, b2 = Cassie3dBatch(n), Cassie3dBatch(n)
+    b1.step(a.cuda(), n=10)
+    q1, v1 = b1.state()
+    ah = a.pin_memory(); qh = torch.empty((n, 21)).pin_memory(); vh = torch.empty((n, 20)).pin_memory()
+    dh = torch.empty(n, dtype=torch.uint8).pin_memory()
+    b2.step_host(ah, qh, vh, dh, n=10)
+    assert torch.equal(q1.cpu(), qh) and torch.equal(v1.cpu(), vh)
+    b1.close(); b2.close()
