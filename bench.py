@@ -78,7 +78,9 @@ def kernel_source_hash():
     h = hashlib.sha256()
     d = os.path.join(ROOT, "cassierl_b200", "csrc")
     for f in sorted(os.listdir(d)):
-        if f.endswith((".cuh", ".cu", ".h")):
+        # the sources the planar step / squat kernels are compiled from (not the 3-D tree engine, the rollout kernels,
+        # the host-side flattener or the C-ABI glue: edits there cannot change the captured kernel)
+        if f.endswith((".cuh", ".cu", ".h")) and not f.startswith(("tree_", "cassie3d", "rollout_", "mjcf_flatten", "cassie2d_api")):
             h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
 

@@ -4,12 +4,15 @@
 // in MuJoCo's dof order (file order); the engine's depth order is internal (TreeModel::user_dof).
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "tree_engine.cuh"
 
 namespace cassie {
 void count_launch();
 namespace tree {
+
+constexpr int kTreeMaxBlock = 384;
 
 template <typename T>
 struct TreeBatchView {
@@ -32,7 +35,7 @@ struct TreeStepArgs {
 };
 
 template <typename T, int LANES>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kTreeMaxBlock)
 k_tree_step(const TreeModel<T>* __restrict__ gm, const TreeBatchView<T> v, const T* __restrict__ action, int n_sub, T z_done,
             int auto_reset, uint8_t* __restrict__ done, const T* __restrict__ reset_q, const T* __restrict__ reset_qd) {
   __shared__ TreeModel<T> m;
@@ -108,14 +111,30 @@ struct TreeLaunch {
 
 template <typename T, int LANES>
 inline cudaError_t launch_tree_step(const TreeModel<T>* dm, const TreeBatchView<T>& v, const TreeStepArgs& a, cudaStream_t s) {
-  constexpr int block = 128, tiles = block / LANES;
-  const size_t dyn = (size_t)tiles * sizeof(Scratch<T>);
-  static bool once = [&] {
-    cudaFuncSetAttribute(k_tree_step<T, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  // Envs (tiles) per CTA: shared memory is the resource (one Scratch block per env + one model copy per CTA).  Default:
+  // two resident CTAs per SM, each with as many tiles as fit; CASSIE3D_TILES overrides.  Whole warps only.
+  static int tiles = 0;
+  if (tiles == 0) {
+    int dev = 0, smem_sm = 0, smem_blk = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const int per_warp = 32 / LANES;
+    const int fixed = (int)sizeof(TreeModel<T>) + 1024;            // static model copy + the per-CTA reservation
+    int t = (smem_sm / 2 - fixed) / (int)sizeof(Scratch<T>);
+    if (const char* e = getenv("CASSIE3D_TILES")) t = atoi(e);
+    const int cap_blk = (smem_blk - (int)sizeof(TreeModel<T>)) / (int)sizeof(Scratch<T>), cap_thr = kTreeMaxBlock / LANES;
+    if (t > cap_blk) t = cap_blk;
+    if (t > cap_thr) t = cap_thr;
+    t = t / per_warp * per_warp;
+    if (t < per_warp) t = per_warp;
+    if ((size_t)t * sizeof(Scratch<T>) + sizeof(TreeModel<T>) > (size_t)smem_blk) return cudaErrorInvalidConfiguration;
+    cudaFuncSetAttribute(k_tree_step<T, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)t * sizeof(Scratch<T>)));
     cudaFuncSetAttribute(k_tree_step<T, LANES>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    return true;
-  }();
-  (void)once;
+    tiles = t;
+  }
+  const int block = tiles * LANES;
+  const size_t dyn = (size_t)tiles * sizeof(Scratch<T>);
   const unsigned grid = (unsigned)((v.n + tiles - 1) / tiles);
   k_tree_step<T, LANES><<<grid, block, dyn, s>>>(dm, v, (const T*)a.action, a.n_sub, (T)a.z_done, a.auto_reset, a.done,
                                                    (const T*)a.reset_q, (const T*)a.reset_qd);

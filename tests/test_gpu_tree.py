@@ -106,7 +106,7 @@ def test_tree_fp32_single_step_vs_oracle(oracle, omodel3d, lanes):
     b.close()
     errs, same = np.array(errs), np.array(same)
     ok = errs[same]
-    assert np.median(ok) < 5e-6 and np.quantile(ok, 0.95) < 1e-5, (np.median(ok), np.quantile(ok, 0.95))
+    assert np.median(ok) < 2e-6 and np.quantile(ok, 0.99) < 1e-5, (np.median(ok), np.quantile(ok, 0.99))
     assert ok.max() < 1e-4, ok.max()
     assert (~same).mean() < 0.02, (~same).mean()
 
@@ -132,7 +132,7 @@ def test_tree_config4_shard_invariants():
     assert (q[:, 2] > 0.3).all()                       # nobody is left lying on the floor
     assert fell.sum() > n // 4 and (b.resets() == fell.to(torch.int32)).all()
     assert (d != 2).all()                              # no env went non-finite
-    assert st[:, 3].sum().item() <= n // 100           # capacity drops are rare
+    assert (st[:, 3] > 0).float().mean().item() < 0.05  # envs that ever dropped a contact for capacity are rare
     b.close()
 
 

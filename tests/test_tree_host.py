@@ -160,9 +160,9 @@ def test_tree_fp32_single_step(oracle, omodel3d, tree_harness):
     U = np.repeat(rng.uniform(-1, 1, (40, 10)) * TORQUE_HIGH_3D, 10, axis=0)
     e, mism, _ = _run(oracle, omodel3d, tree_harness, U, True, True, pose3d())
     same = e[~mism]
-    assert np.median(same) < 5e-6, np.median(same)
-    assert np.quantile(same, 0.95) < 1e-5, np.quantile(same, 0.95)
-    assert same.max() < 5e-5, same.max()
+    assert np.median(same) < 1e-6, np.median(same)
+    assert np.quantile(same, 0.99) < 1e-5, np.quantile(same, 0.99)        # the 1e-5 bar holds on >= 99 % of the steps
+    assert same.max() < 5e-5, same.max()                                  # the rest: a contact at its first touch
     assert mism.sum() <= 8, mism.sum()
     assert e.max() < 2e-2
 

@@ -15,3 +15,13 @@ python tools/summarize_ncu.py /tmp/${TAG}_tree.ncu-rep > gpurun_out/${TAG}_tree.
 ncu -i /tmp/${TAG}_tree.ncu-rep --page raw --csv > gpurun_out/${TAG}_tree_raw.csv 2>/dev/null
 ncu -i /tmp/${TAG}_tree.ncu-rep --page source --csv 2>/dev/null | gzip > gpurun_out/${TAG}_tree_source.csv.gz
 head -36 gpurun_out/${TAG}_tree.txt
+echo "== tensor-core MLP A/B (thread-engine rollout kernel, PD action space)"
+timeout 600 python -m pytest tests/test_gpu_rollout.py -m gpu -q -x 2>&1 | tail -4 | tee gpurun_out/${TAG}_pytest_rollout.txt
+for v in scalar tc scalar tc; do
+  CASSIE_MLP=$v timeout 300 python tools/bench_rollout.py --mode PD --T 20 --reps 7 2>&1 | tail -1 > gpurun_out/${TAG}_rollout_mlp_${v}.json
+  python -c "import json; d=json.load(open('gpurun_out/${TAG}_rollout_mlp_${v}.json')); print('mlp $v env-steps/s %.4g collect_ms %.3f' % (d['env_steps_per_s'], d['collect_ms']))"
+done | tee gpurun_out/${TAG}_mlp_ab.txt
+for v in scalar tc; do
+  CASSIE_MLP=$v timeout 300 python tools/bench_rollout.py --mode PD --task imitate --T 20 --reps 7 2>&1 | tail -1 > gpurun_out/${TAG}_rollout_mlp_imitate_${v}.json
+  python -c "import json; d=json.load(open('gpurun_out/${TAG}_rollout_mlp_imitate_${v}.json')); print('mlp $v (imitate, 26 inputs) env-steps/s %.4g collect_ms %.3f' % (d['env_steps_per_s'], d['collect_ms']))"
+done | tee -a gpurun_out/${TAG}_mlp_ab.txt
