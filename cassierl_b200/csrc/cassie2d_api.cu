@@ -73,6 +73,10 @@ struct CassieBatch {
   void* d_state26 = nullptr;       // real [n][26]
   void* d_phase = nullptr;         // real [n]
   double* d_traj = nullptr;
+  double* d_traj_qvel = nullptr;   // [rows][13] velocities of the reference trajectory (random-phase reset), may be null
+  double* d_traj_time = nullptr;   // [rows]
+  double* d_sample_time = nullptr; // [n] staging: env clock of the sampled row
+  void* d_state18 = nullptr;       // real [n][18] staging of the sampled reset's observation
   cudaStream_t own_stream = nullptr;
   size_t real_size() const { return precision == 64 ? 8 : 4; }
 };
@@ -132,6 +136,82 @@ static int upload_state(CassieBatch* h, const double* s26, cudaStream_t st) {
 
 static int set_device(const CassieBatch* h) {
   CU_OK(cudaSetDevice(h->device));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Random-phase reset (Cassie3dTraj.sample(), rllab/envs/cassie2d_trajectory.py:26-28: i = randrange(len(time)),
+// returns time[i], qpos[i], qvel[i]) on the device: Philox4x32-10 keyed by (seed, global env id, draw) picks the row.
+namespace {
+__host__ __device__ inline uint32_t philox_first(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1) {
+  uint32_t c[4] = {c0, c1, c2, 0x53414d50u};   // "SAMP": a stream of its own, apart from the action noise
+  for (int r = 0; r < 10; r++) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c[0];
+}
+// StateGeneral order: base pos[3], base vel[3], left pos[5], left vel[5], right pos[5], right vel[5]
+template <typename T>
+__global__ void k_sample_state26(int n, const double* __restrict__ tq, const double* __restrict__ tv, const double* __restrict__ tt,
+                                 int rows, double tmax, uint64_t seed, uint32_t env0, uint32_t draw, const uint8_t* __restrict__ mask,
+                                 T* __restrict__ state26, double* __restrict__ time_out, int32_t* __restrict__ index_out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n || (mask && !mask[e])) return;
+  const int i = (int)(philox_first(env0 + (uint32_t)e, draw, 0u, (uint32_t)seed, (uint32_t)(seed >> 32)) % (uint32_t)rows);
+  const double* q = tq + (size_t)i * 13;
+  T* s = state26 + (size_t)e * 26;
+  for (int k = 0; k < 3; k++) { s[k] = (T)q[k]; s[3 + k] = tv ? (T)tv[(size_t)i * 13 + k] : T(0); }
+  for (int L = 0; L < 2; L++)
+    for (int k = 0; k < 5; k++) {
+      s[6 + 10 * L + k] = (T)q[3 + 5 * L + k];
+      s[11 + 10 * L + k] = tv ? (T)tv[(size_t)i * 13 + 3 + 5 * L + k] : T(0);
+    }
+  time_out[e] = tt ? tt[i] : tmax * (double)i / (double)rows;
+  if (index_out) index_out[e] = i;
+}
+// episode bookkeeping of the sampled reset + the observation reset() returns (cassie2d.py:78-95: the 17 pos-invariant
+// slots, reference slots 17..25 zero; cassie2d_structs.py:68-75)
+template <typename T>
+__global__ void k_sample_finish(BatchView<T> v, const double* __restrict__ time_in, const uint8_t* __restrict__ mask, int task,
+                                const T* __restrict__ s18, T* __restrict__ obs) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= v.n || (mask && !mask[e])) return;
+  const size_t n = (size_t)v.n;
+  v.clock[e] = time_in[e];
+  v.ep_len[e] = 0;
+  v.qp_set[e] = 0u;
+  for (int i = 0; i < 13; i++) v.warm[(size_t)i * n + e] = T(0);
+  v.jsum0[e] = v.qpos[3 * n + e] + v.qpos[4 * n + e] + v.qpos[6 * n + e] + v.qpos[8 * n + e] + v.qpos[9 * n + e] + v.qpos[11 * n + e];
+  if (obs) {
+    const T* s = s18 + (size_t)e * 18;
+    const int od = task == 1 ? 26 : 17;
+    T* o = obs + (size_t)e * od;
+    for (int i = 0; i < 17; i++) o[i] = s[i + 1];
+    o[5] -= s[0];
+    o[11] -= s[0];
+    for (int i = 17; i < od; i++) o[i] = T(0);
+  }
+}
+}  // namespace
+
+template <typename R>
+static int sampled_reset(CassieBatch* h, int task, unsigned long long seed, unsigned int env0, unsigned int draw,
+                         const uint8_t* mask_dev, int32_t* index_out_dev, void* obs_dev, cudaStream_t st) {
+  const int n = h->n, grid = (n + 127) / 128;
+  k_sample_state26<R><<<grid, 128, 0, st>>>(n, h->d_traj, h->d_traj_qvel, h->d_traj_time, BV<R>(h).traj_rows, BV<R>(h).traj_tmax,
+                                            (uint64_t)seed, env0, draw, mask_dev, (R*)h->d_state26, h->d_sample_time, index_out_dev);
+  count_launch();
+  CU_OK(cudaGetLastError());
+  CU_OK(Launch<R>::reset(BV<R>(h), (const R*)h->d_state26, 1, mask_dev, st));
+  CU_OK(Launch<R>::refresh_op(MP<R>(h), BV<R>(h), mask_dev, st));
+  if (obs_dev) CU_OK(Launch<R>::get_op(BV<R>(h), (R*)h->d_state18, st));
+  k_sample_finish<R><<<grid, 128, 0, st>>>(BV<R>(h), h->d_sample_time, mask_dev, task, (const R*)h->d_state18, (R*)obs_dev);
+  count_launch();
+  CU_OK(cudaGetLastError());
   return 0;
 }
 
@@ -278,6 +358,43 @@ int Cassie2dBatchSetTrajectory(CassieBatch* h, const double* qpos_rows_host, int
   h->v32.traj_rows = h->v64.traj_rows = n_rows;
   h->v32.traj_tmax = h->v64.traj_tmax = t_max;
   return 0;
+}
+
+int Cassie2dBatchSetTrajectoryDetail(CassieBatch* h, const double* qvel_rows_host, const double* time_rows_host, int n_rows) {
+  if (!h) return fail("null handle");
+  if (!h->d_traj || n_rows != h->v32.traj_rows) return fail("SetTrajectoryDetail: call Cassie2dBatchSetTrajectory first, with the same row count");
+  if (set_device(h)) return -1;
+  CU_OK(cudaDeviceSynchronize());
+  if (h->d_traj_qvel) { cudaFree(h->d_traj_qvel); h->d_traj_qvel = nullptr; }
+  if (h->d_traj_time) { cudaFree(h->d_traj_time); h->d_traj_time = nullptr; }
+  if (qvel_rows_host) {
+    CU_OK(cudaMalloc((void**)&h->d_traj_qvel, sizeof(double) * 13 * (size_t)n_rows));
+    CU_OK(cudaMemcpy(h->d_traj_qvel, qvel_rows_host, sizeof(double) * 13 * (size_t)n_rows, cudaMemcpyHostToDevice));
+  }
+  if (time_rows_host) {
+    CU_OK(cudaMalloc((void**)&h->d_traj_time, sizeof(double) * (size_t)n_rows));
+    CU_OK(cudaMemcpy(h->d_traj_time, time_rows_host, sizeof(double) * (size_t)n_rows, cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+int Cassie2dBatchEnvResetSampled(CassieBatch* h, int task, unsigned long long seed, unsigned int first_global_env,
+                                 unsigned int draw, const uint8_t* mask_dev, int32_t* index_out_dev, void* obs_dev, void* stream) {
+  if (!h) return fail("null handle");
+  if (task != 0 && task != 1) return fail("bad task");
+  if (!h->d_traj) return fail("random-phase reset needs Cassie2dBatchSetTrajectory first");
+  if (set_device(h)) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = h->n;
+  if (!h->d_sample_time) {
+    CU_OK(cudaMalloc((void**)&h->d_sample_time, sizeof(double) * (size_t)n));
+    h->allocs.push_back(h->d_sample_time);
+    CU_OK(cudaMalloc(&h->d_state18, h->real_size() * 18 * (size_t)n));
+    h->allocs.push_back(h->d_state18);
+  }
+  int rc = 0;
+  DISPATCH(h, rc = sampled_reset<R>(h, task, seed, first_global_env, draw, mask_dev, index_out_dev, obs_dev, st));
+  return rc;
 }
 
 // action-space boxes of the reference envs (cassie_stand2d.py:255-268 == cassie2d.py:353-368)

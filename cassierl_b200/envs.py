@@ -216,6 +216,28 @@ class Cassie2dBatchEnv:
             _lib.check(b.L.Cassie2dBatchEnvReset(b.h, self.task, self.flags, self._obs.data_ptr(), _stream_ptr()), "EnvReset")
         return self._obs
 
+    def reset_sampled(self, seed=1, draw=0, mask=None, first_global_env=0, trajectory=None, want_index=False):
+        """Random-phase reset: every env (or the masked ones) restarts at a random row of the reference trajectory --
+        Cassie2dTraj.sample() (rllab/envs/cassie2d_trajectory.py:26-28) on the device, Philox-keyed by (seed, global env
+        id, draw).  Returns the observation (and the sampled row indices with want_index)."""
+        b = self.batch
+        dp = _lib.ct.POINTER(_lib.ct.c_double)
+        if not getattr(self, "_traj_detail", False):
+            tr = trajectory if trajectory is not None else Cassie2dTraj()
+            q = np.ascontiguousarray(tr.qpos, np.float64)
+            v = np.ascontiguousarray(tr.qvel, np.float64); t = np.ascontiguousarray(tr.time, np.float64)
+            if self.task != _lib.TASK_IMITATE:
+                _lib.check(b.L.Cassie2dBatchSetTrajectory(b.h, q.ctypes.data_as(dp), q.shape[0], float(tr.time[-1])), "SetTrajectory")
+            _lib.check(b.L.Cassie2dBatchSetTrajectoryDetail(b.h, v.ctypes.data_as(dp), t.ctypes.data_as(dp), q.shape[0]), "SetTrajectoryDetail")
+            self._traj_detail = True
+        idx = torch.empty(b.n, dtype=torch.int32, device=b.device) if want_index else None
+        m = None if mask is None else mask.to(device=b.device, dtype=torch.uint8).contiguous()
+        with torch.cuda.device(b.device):
+            _lib.check(b.L.Cassie2dBatchEnvResetSampled(b.h, self.task, int(seed), int(first_global_env), int(draw),
+                                                        None if m is None else m.data_ptr(), None if idx is None else idx.data_ptr(),
+                                                        self._obs.data_ptr(), _stream_ptr()), "EnvResetSampled")
+        return (self._obs, idx) if want_index else self._obs
+
     def step(self, action, n=10):
         """-> obs, reward, done.  With auto_reset a done env has already been reset when the call returns and its
         obs is the one env.reset() gives (so the next action is computed for the new episode); terminal_obs=True

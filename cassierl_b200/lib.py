@@ -22,6 +22,7 @@ BATCH_SYMBOLS = ["CassieGetLastError", "Cassie2dBatchInit", "Cassie2dBatchDestro
                  "Cassie2dBatchPrecision", "Cassie2dBatchDevice", "Cassie2dBatchRealSize", "Cassie2dBatchReset",
                  "Cassie2dBatchSetState", "Cassie2dBatchGetGeneralState", "Cassie2dBatchGetOperationalSpaceState",
                  "Cassie2dBatchStep", "Cassie2dBatchEnvStep", "Cassie2dBatchEnvReset", "Cassie2dBatchSetTrajectory",
+                 "Cassie2dBatchSetTrajectoryDetail", "Cassie2dBatchEnvResetSampled",
                  "Cassie2dBatchSquat", "Cassie2dBatchRollout", "Cassie2dBatchDiscountedReturns", "Cassie2dBatchBaselineMoments", "Cassie2dBatchAdvantages", "Cassie2dBatchStepHost", "Cassie2dBatchEnvStepHost", "Cassie2dBatchSquatHost",
                  "Cassie2dBatchGetStats", "Cassie2dBatchGetEpisodeLengths", "Cassie2dBatchSetWarmStart", "Cassie2dBatchGetWarmStart", "Cassie2dBatchSync", "CassieMeasureFp32Peak", "CassieKernelLaunchCount"]
 
@@ -59,6 +60,8 @@ def load():
     L.Cassie2dBatchEnvStep.argtypes = [vp, ci, ci, vp, ci, ci, vp, vp, vp, vp]
     L.Cassie2dBatchEnvReset.argtypes = [vp, ci, ci, vp, vp]
     L.Cassie2dBatchSetTrajectory.argtypes = [vp, ct.POINTER(cd), ci, cd]
+    L.Cassie2dBatchSetTrajectoryDetail.argtypes = [vp, ct.POINTER(cd), ct.POINTER(cd), ci]
+    L.Cassie2dBatchEnvResetSampled.argtypes = [vp, ci, ct.c_ulonglong, ct.c_uint, ct.c_uint, vp, vp, vp, vp]
     L.Cassie2dBatchSquat.argtypes = [vp, ci, ci, vp, vp, vp]
     L.Cassie2dBatchDiscountedReturns.argtypes = [vp, vp, vp, vp, cd, ci, vp, vp]
     L.Cassie2dBatchBaselineMoments.argtypes = [vp, ci, vp, vp, vp, vp, ci, vp, vp, vp]

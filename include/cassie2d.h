@@ -131,6 +131,17 @@ int Cassie2dBatchEnvReset(CassieBatch* h, int task, int flags, void* obs_dev, vo
  * Cassie2dTraj.qpos (cassie2d_trajectory.py:31-134), plus t_max = time[-1] and the row count
  * used by state(t) (:16-19). */
 int Cassie2dBatchSetTrajectory(CassieBatch* h, const double* qpos_rows_host, int n_rows, double t_max);
+/* optional companions of the table for the random-phase reset: Cassie2dTraj.qvel ([n_rows][13]) and .time ([n_rows]);
+ * either may be NULL (zero velocities / time[i] = i * t_max / n_rows) */
+int Cassie2dBatchSetTrajectoryDetail(CassieBatch* h, const double* qvel_rows_host, const double* time_rows_host, int n_rows);
+/* Random-phase reset = Cassie3dTraj.sample() (cassie2d_trajectory.py:26-28: i = randrange(len(time)); time[i], qpos[i],
+ * qvel[i]) for every env (mask NULL) or the masked envs, on the device: row i = Philox4x32-10(seed; global env id =
+ * first_global_env + e, draw) mod n_rows, so the draw does not depend on the launch partition or the GPU count.  The env
+ * restarts at that row: qpos / qvel from the table, env clock = time[i], episode length 0, lagged operational-space
+ * state refreshed, warm start and QP partition cleared.  index_out_dev (int32 [n]) and obs_dev (the observation reset()
+ * returns: reference slots zero) may be NULL. */
+int Cassie2dBatchEnvResetSampled(CassieBatch* h, int task, unsigned long long seed, unsigned int first_global_env,
+                                 unsigned int draw, const uint8_t* mask_dev, int32_t* index_out_dev, void* obs_dev, void* stream);
 
 /* Rollout collection (BASELINE configs[4]): what rllab's sampler does around the reference env
  * (rllab/envs/trpo_cassie.py:13-55: GaussianMLPPolicy(hidden_sizes=(32,32)).get_action ->

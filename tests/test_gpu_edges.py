@@ -234,3 +234,61 @@ def test_imitation_reset_observation_has_zero_reference_slots(E, LIB):
     o, _, _ = env.step(a)
     assert (o[:, 17:] != 0).any()
     env.terminate()
+
+
+def philox_first(c0, c1, c2, k0, k1):
+    """numpy restatement of csrc/cassie2d_api.cu philox_first (Philox4x32-10, counter (c0, c1, c2, 'SAMP'))"""
+    c = [np.uint64(c0), np.uint64(c1), np.uint64(c2), np.uint64(0x53414D50)]
+    k0 = np.uint64(k0); k1 = np.uint64(k1); M = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c[0]; p1 = np.uint64(0xCD9E8D57) * c[2]
+        c = [((p1 >> np.uint64(32)) ^ c[1] ^ k0) & M, p1 & M, ((p0 >> np.uint64(32)) ^ c[3] ^ k1) & M, p0 & M]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & M; k1 = (k1 + np.uint64(0xBB67AE85)) & M
+    return int(c[0])
+
+
+def test_random_phase_reset_on_device():
+    """Cassie2dTraj.sample() on the device (cassie2d_trajectory.py:26-28): the sampled rows follow the documented Philox
+    stream, every env restarts exactly at its row (qpos, qvel, env clock), the draw is invariant to the sharding, the
+    mask leaves the other envs alone, and the first imitation reward uses the clock of the sampled row."""
+    import torch
+    from cassierl_b200 import envs
+    from cassierl_b200.trajectory import Cassie2dTraj
+    tr = Cassie2dTraj()
+    rows = len(tr.time)
+    n = 257
+    env = envs.Cassie2dBatchEnv(n, task="imitate", control_mode="PD", precision=64)
+    env.reset()
+    obs, idx = env.reset_sampled(seed=77, draw=3, first_global_env=1000, want_index=True)
+    idx = idx.cpu().numpy()
+    want = np.array([philox_first(1000 + e, 3, 0, 77, 0) % rows for e in range(n)])
+    assert (idx == want).all()
+    assert len(np.unique(idx)) > n // 2 and idx.min() >= 0 and idx.max() < rows
+    s = env.batch.get_general_state().cpu().numpy()
+    q = np.concatenate([s[:, 0:3], s[:, 6:11], s[:, 16:21]], axis=1); v = np.concatenate([s[:, 3:6], s[:, 11:16], s[:, 21:26]], axis=1)
+    assert np.abs(q - tr.qpos[idx]).max() == 0 and np.abs(v - tr.qvel[idx]).max() == 0
+    o = obs.cpu().numpy()
+    assert np.isfinite(o).all() and (o[:, 17:] == 0).all()            # reset(): reference slots are zero
+    assert np.abs(o[:, 0] - tr.qpos[idx, 1]).max() < 1e-12              # obs[0] = pelvis z
+    # sharding invariance: a sub-batch with the matching global offset draws the same rows
+    env2 = envs.Cassie2dBatchEnv(64, task="imitate", control_mode="PD", precision=64)
+    env2.reset()
+    _, idx2 = env2.reset_sampled(seed=77, draw=3, first_global_env=1000 + 100, want_index=True)
+    assert (idx2.cpu().numpy() == idx[100:164]).all()
+    # mask: only the flagged envs move
+    mask = torch.zeros(n, dtype=torch.uint8); mask[::2] = 1
+    before = env.batch.get_general_state().clone()
+    _, idx3 = env.reset_sampled(seed=78, draw=0, first_global_env=1000, mask=mask, want_index=True)
+    after = env.batch.get_general_state()
+    assert torch.equal(after[1::2], before[1::2]) and not torch.equal(after[::2], before[::2])
+    # the env clock is the sampled row's time: one policy step later the reference row is index(time[i] + 10 dt)
+    a = torch.tensor(np.tile(tr.qpos[0, [3, 4, 6, 8, 9, 11]], (64, 1)), dtype=torch.float64, device="cuda")
+    o2, _, _ = env2.step(a, n=10)
+    t1 = tr.time[idx2.cpu().numpy()] + 10 * 0.0005
+    ref_rows = np.array([tr.index(t) for t in t1])
+    near = np.array([min(abs(int(r) - int(tr.index(t - 1e-9))), abs(int(r) - int(tr.index(t + 1e-9)))) for r, t in zip(ref_rows, t1)])
+    got = o2.cpu().numpy()[:, 17:]
+    exp = tr.qpos[ref_rows][:, [0, 1, 2, 3, 4, 6, 8, 9, 11]]
+    ok = np.abs(got - exp).max(axis=1) < 1e-12
+    assert ok[near == 0].all() and ok.mean() > 0.9        # rows whose index sits on a floating-point boundary may differ by one
+    env.terminate(); env2.terminate()
