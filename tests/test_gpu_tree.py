@@ -49,7 +49,7 @@ def test_tree_fp64_rollout_vs_oracle(oracle, omodel3d, lanes):
     _, qo, vo, _ = oracle.rollout_tree(omodel3d, q0, v0, steps, actions=A, hold=hold)
     e = _err(q, v, qo, vo)
     assert e.max() < 1e-9, e
-    assert st[:, 0].max() >= 12 and st[:, 3].sum() == 0
+    assert st[:, 0].max() >= 9 and st[:, 3].sum() == 0      # rows of the LAST step: connects + at least one floor contact somewhere
 
 
 def test_tree_fp64_fall_and_autoreset_bit_exact(oracle, omodel3d):
@@ -121,7 +121,7 @@ def test_tree_config4_shard_invariants():
     g = torch.Generator(device="cuda").manual_seed(0)
     hi = torch.tensor(HI, dtype=torch.float32, device="cuda")
     fell = torch.zeros(n, dtype=torch.int64, device="cuda")
-    for k in range(60):
+    for k in range(130):        # 1300 simulator steps: under random torques nearly every robot has fallen once by then
         a = (torch.rand((n, 10), generator=g, device="cuda") * 2 - 1) * hi
         d = b.step(a, n=10, z_done=0.5, auto_reset=True)
         fell += (d != 0)

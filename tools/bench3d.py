@@ -24,7 +24,7 @@ p.add_argument("--warmup", type=int, default=3)
 p.add_argument("--substeps", type=int, default=10)
 p.add_argument("--lanes", type=int, default=0)
 p.add_argument("--precision", type=int, default=32)
-p.add_argument("--preadvance", type=int, default=300, help="simulator steps before timing (robots land, some fall and reset)")
+p.add_argument("--preadvance", type=int, default=2000, help="simulator steps before timing: robots fall after ~1000 steps of random torques and reset, by 2000 the batch is a mix of phases")
 p.add_argument("--no-cpu-baseline", action="store_true")
 p.add_argument("--cpu-seconds", type=float, default=10.0)
 a = p.parse_args()

@@ -9,7 +9,7 @@ for lanes in 32 16 8; do
   python -c "import json; d=json.load(open('gpurun_out/${TAG}_bench3d_l${lanes}.json')); print('lanes $lanes value %.4g e2e %.4g frac %.4f ms %.3f' % (d['value'], d['e2e']['value'], d['roofline']['frac'], d['ms_per_step']), d['stats'])" 2>&1 | tail -1
 done | tee gpurun_out/${TAG}_lanes.txt
 echo "== ncu"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_tree_step -s 34 -c 1 -f -o /tmp/${TAG}_tree \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_tree_step -s 201 -c 1 -f -o /tmp/${TAG}_tree \
   python tools/bench3d.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_tree_ncu.log 2>&1
 python tools/summarize_ncu.py /tmp/${TAG}_tree.ncu-rep > gpurun_out/${TAG}_tree.txt 2>&1
 ncu -i /tmp/${TAG}_tree.ncu-rep --page raw --csv > gpurun_out/${TAG}_tree_raw.csv 2>/dev/null
