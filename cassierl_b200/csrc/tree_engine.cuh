@@ -646,71 +646,75 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
     for (int i = 0; i < nefc;) {
       const int type = s.r_type[i];
       const int dim = type == kRowContact ? s.c_dim[s.r_id[i]] : 1;
-      T res[3], old[3], fn[3], At[9];
-      for (int j = 0; j < dim; j++) {
-        res[j] = s.r_acc[i + j];
-        old[j] = s.r_f[i + j];
-        fn[j] = old[j];
-        for (int c = 0; c < dim; c++) At[3 * j + c] = s.Am[tri(i + j, i + c)];
-      }
+      const int di = i * (i + 1) / 2 + i;                 // packed index of A[i][i]
       if (dim == 1) {
-        fn[0] -= res[0] / At[0];
-        if (type != kRowEq && fn[0] < 0) fn[0] = 0;
+        // ---- scalar row: connect, joint limit, frictionless contact
+        const T res = s.r_acc[i], old = s.r_f[i], aii = s.Am[di];
+        T fn = old - res / aii;
+        if (type != kRowEq && fn < 0) fn = 0;
+        T d0 = fn - old;
+        T change = (T)0.5 * d0 * d0 * aii + d0 * res;      // costChange: revert an update that raises the dual cost
+        if (change > (T)1e-10) { d0 = 0; change = 0; }
+        improvement -= change;
+        if (d0 != 0) {                                      // uniform in the tile: every lane holds the same d0
+          tl.sync();                                        // every lane has read this row's residual and force
+          if (tl.lane == 0) s.r_f[i] = old + d0;
+          for (int r = tl.lane; r < nefc; r += LANES) s.r_acc[r] += s.Am[tri(i, r)] * d0;
+          tl.sync();
+        }
+        i += 1;
+        continue;
+      }
+      // ---- condim-3 contact, elliptic cone: rows i (normal), i + 1, i + 2 (tangents); A block symmetric
+      const int d1 = di + i + 1, d2 = d1 + i + 2;           // rows i + 1 and i + 2 start i + 1 and 2 i + 3 entries further on
+      const T a00 = s.Am[di], a10 = s.Am[d1], a11 = s.Am[d1 + 1], a20 = s.Am[d2], a21 = s.Am[d2 + 1], a22 = s.Am[d2 + 2];
+      const T r0 = s.r_acc[i], r1 = s.r_acc[i + 1], r2 = s.r_acc[i + 2];
+      const T o0 = s.r_f[i], o1 = s.r_f[i + 1], o2 = s.r_f[i + 2];
+      T f0 = o0, f1 = o1, f2 = o2;
+      const T* frc = m.pair_friction[s.c_pair[s.r_id[i]]];
+      const T mu2[2] = {frc[0], frc[0]};
+      if (f0 < (T)kMinVal) {
+        f0 -= r0 / a00;
+        if (f0 < 0) f0 = 0;
+        f1 = f2 = 0;
       } else {
-        const T* frc = m.pair_friction[s.c_pair[s.r_id[i]]];
-        const T mu2[2] = {frc[0], frc[0]};
-        if (fn[0] < (T)kMinVal) {
-          fn[0] -= res[0] / At[0];
-          if (fn[0] < 0) fn[0] = 0;
-          fn[1] = fn[2] = 0;
-        } else {
-          T v1[3], denom = 0;
-          for (int j = 0; j < 3; j++) v1[j] = At[3 * j] * fn[0] + At[3 * j + 1] * fn[1] + At[3 * j + 2] * fn[2];
-          for (int j = 0; j < 3; j++) denom += fn[j] * v1[j];
-          if (denom >= (T)kMinVal) {
-            T x = -(fn[0] * res[0] + fn[1] * res[1] + fn[2] * res[2]) / denom;
-            if (fn[0] + x * fn[0] < 0) x = -1;
-            const T v0 = fn[0], va = fn[1], vb = fn[2];
-            fn[0] += x * v0; fn[1] += x * va; fn[2] += x * vb;
-          }
-        }
-        // tangential update with the normal force fixed
-        T Ac[4] = {At[4], At[5], At[7], At[8]}, bc[2], v[2];
-        for (int j = 0; j < 2; j++) {
-          bc[j] = res[1 + j] - Ac[2 * j] * old[1] - Ac[2 * j + 1] * old[2];
-          bc[j] += At[3 * (j + 1)] * (fn[0] - old[0]);
-        }
-        if (fn[0] < (T)kMinVal) fn[1] = fn[2] = 0;
-        else {
-          const int active = qcqp2(v, Ac, bc, mu2, fn[0]);
-          if (active) {
-            T sc = v[0] * v[0] / (mu2[0] * mu2[0]) + v[1] * v[1] / (mu2[1] * mu2[1]);
-            sc = sqrt(fn[0] * fn[0] / fmax((T)kMinVal, sc));
-            v[0] *= sc; v[1] *= sc;
-          }
-          fn[1] = v[0]; fn[2] = v[1];
+        // ray update: scale the whole force along its own direction
+        const T v0 = a00 * f0 + a10 * f1 + a20 * f2, v1 = a10 * f0 + a11 * f1 + a21 * f2, v2 = a20 * f0 + a21 * f1 + a22 * f2;
+        const T denom = f0 * v0 + f1 * v1 + f2 * v2;
+        if (denom >= (T)kMinVal) {
+          T x = -(f0 * r0 + f1 * r1 + f2 * r2) / denom;
+          if (f0 + x * f0 < 0) x = -1;
+          const T g0 = f0, g1 = f1, g2 = f2;
+          f0 += x * g0; f1 += x * g1; f2 += x * g2;
         }
       }
-      // costChange: revert an update that raises the dual cost
-      T delta[3] = {0, 0, 0}, change = 0;
-      for (int j = 0; j < dim; j++) delta[j] = fn[j] - old[j];
-      for (int j = 0; j < dim; j++) {
-        T v = 0;
-        for (int c = 0; c < dim; c++) v += At[3 * j + c] * delta[c];
-        change += (T)0.5 * delta[j] * v + delta[j] * res[j];
+      // tangential update with the normal force fixed
+      if (f0 < (T)kMinVal) f1 = f2 = 0;
+      else {
+        const T Ac[4] = {a11, a21, a21, a22};
+        const T bc[2] = {r1 - a11 * o1 - a21 * o2 + a10 * (f0 - o0), r2 - a21 * o1 - a22 * o2 + a20 * (f0 - o0)};
+        T v[2];
+        const int active = qcqp2(v, Ac, bc, mu2, f0);
+        if (active) {
+          T sc = v[0] * v[0] / (mu2[0] * mu2[0]) + v[1] * v[1] / (mu2[1] * mu2[1]);
+          sc = sqrt(f0 * f0 / fmax((T)kMinVal, sc));
+          v[0] *= sc; v[1] *= sc;
+        }
+        f1 = v[0]; f2 = v[1];
       }
-      if (change > (T)1e-10) { for (int j = 0; j < dim; j++) delta[j] = 0; change = 0; }
+      T e0 = f0 - o0, e1 = f1 - o1, e2 = f2 - o2;
+      T change = (T)0.5 * (e0 * (a00 * e0 + a10 * e1 + a20 * e2) + e1 * (a10 * e0 + a11 * e1 + a21 * e2) + e2 * (a20 * e0 + a21 * e1 + a22 * e2)) +
+                 e0 * r0 + e1 * r1 + e2 * r2;
+      if (change > (T)1e-10) { e0 = e1 = e2 = 0; change = 0; }
       improvement -= change;
-      tl.sync();                                   // every lane has read this block's residual and forces
-      if (tl.lane == 0)
-        for (int j = 0; j < dim; j++) s.r_f[i + j] = old[j] + delta[j];
-      for (int r = tl.lane; r < nefc; r += LANES) {
-        T a = s.r_acc[r];
-        for (int j = 0; j < dim; j++) a += s.Am[tri(i + j, r)] * delta[j];
-        s.r_acc[r] = a;
+      if (e0 != 0 || e1 != 0 || e2 != 0) {
+        tl.sync();
+        if (tl.lane == 0) { s.r_f[i] = o0 + e0; s.r_f[i + 1] = o1 + e1; s.r_f[i + 2] = o2 + e2; }
+        for (int r = tl.lane; r < nefc; r += LANES)
+          s.r_acc[r] += s.Am[tri(i, r)] * e0 + s.Am[tri(i + 1, r)] * e1 + s.Am[tri(i + 2, r)] * e2;
+        tl.sync();
       }
-      tl.sync();
-      i += dim;
+      i += 3;
     }
     iter++;
     if (improvement * scale < m.tolerance) break;
