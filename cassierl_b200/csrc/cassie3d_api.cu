@@ -42,7 +42,8 @@ static std::string default_xml3() {
 struct Cassie3dBatch {
   int n = 0, device = 0, precision = 32, lanes = 32;
   TreeModel<double> model;
-  void* d_model = nullptr;
+  TreeModel<float> m32;
+  TreeModel<double> m64;
   TreeBatchView<float> v32;
   TreeBatchView<double> v64;
   std::vector<void*> allocs;
@@ -72,10 +73,9 @@ int dmalloc(Cassie3dBatch* h, void** p, size_t bytes) {
 template <typename T>
 int setup(Cassie3dBatch* h, TreeBatchView<T>& v) {
   const size_t n = (size_t)h->n;
-  TreeModel<T> m;
-  cast_tree_model(&m, h->model);
-  if (dmalloc(h, &h->d_model, sizeof(m))) return -1;
-  CU3_OK(cudaMemcpy(h->d_model, &m, sizeof(m), cudaMemcpyHostToDevice));
+  const TreeModel<double>& m = h->model;
+  cast_tree_model(&h->m32, h->model);
+  cast_tree_model(&h->m64, h->model);
   v.n = h->n;
   if (dmalloc(h, (void**)&v.qpos, sizeof(T) * n * m.nq) || dmalloc(h, (void**)&v.qvel, sizeof(T) * n * m.nv) ||
       dmalloc(h, (void**)&v.warm, sizeof(T) * n * m.nv) || dmalloc(h, (void**)&v.stats, sizeof(int32_t) * 4 * n) ||
@@ -94,6 +94,9 @@ int upload_reset(Cassie3dBatch* h) {
   return 0;
 }
 
+template <typename T> const TreeModel<T>& model_of(Cassie3dBatch* h);
+template <> const TreeModel<float>& model_of<float>(Cassie3dBatch* h) { return h->m32; }
+template <> const TreeModel<double>& model_of<double>(Cassie3dBatch* h) { return h->m64; }
 template <typename T> TreeBatchView<T>& view(Cassie3dBatch* h);
 template <> TreeBatchView<float>& view<float>(Cassie3dBatch* h) { return h->v32; }
 template <> TreeBatchView<double>& view<double>(Cassie3dBatch* h) { return h->v64; }
@@ -103,7 +106,7 @@ int step(Cassie3dBatch* h, const void* action, int n_sub, double z_done, int aut
   TreeStepArgs a;
   a.action = action; a.n_sub = n_sub; a.z_done = z_done; a.auto_reset = auto_reset; a.done = done;
   a.reset_q = h->d_reset_q; a.reset_qd = h->d_reset_qd;
-  CU3_OK(TreeLaunch<T>::step((const TreeModel<T>*)h->d_model, view<T>(h), a, h->lanes, s));
+  CU3_OK(TreeLaunch<T>::step(model_of<T>(h), view<T>(h), a, h->lanes, s));
   return 0;
 }
 }  // namespace

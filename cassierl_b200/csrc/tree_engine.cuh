@@ -287,22 +287,20 @@ TREE_FN void dynamics(const Tile<LANES>& tl, const TreeModel<T>& m, Scratch<T>& 
   tl.sync();
 }
 
-// dense Cholesky of (M + diag(add)) into s.L (lower) and s.dinv = 1 / L_kk
+// dense Cholesky of (M + diag(add)) into s.L (lower triangle) and s.dinv = 1 / L_kk.  Left-looking, one row per
+// lane and ONE tile barrier per column: every lane forms the pivot of column k itself (from row k, complete since the
+// previous barrier), then its own entry L[i][k] = (M[i][k] - sum_j L[i][j] L[k][j]) / L[k][k].
 template <int LANES, typename T>
 TREE_FN void cholesky(const Tile<LANES>& tl, int n, Scratch<T>& s, const T* add, T scale) {
-  for (int i = tl.lane; i < n; i += LANES)
-    for (int j = 0; j <= i; j++) s.L[i * kLD + j] = s.M[i * kLD + j] + (i == j && add ? scale * add[i] : (T)0);
-  tl.sync();
   for (int k = 0; k < n; k++) {
-    const T piv = sqrt(s.L[k * kLD + k]);
-    const T inv = (T)1 / piv;
-    tl.sync();                                    // everybody has read the pivot before lane 0 overwrites it
-    if (tl.lane == 0) { s.L[k * kLD + k] = piv; s.dinv[k] = inv; }
-    for (int i = k + 1 + tl.lane; i < n; i += LANES) s.L[i * kLD + k] *= inv;
-    tl.sync();
+    T d = s.M[k * kLD + k] + (add ? scale * add[k] : (T)0);
+    for (int j = 0; j < k; j++) { const T l = s.L[k * kLD + j]; d -= l * l; }
+    const T inv = (T)1 / sqrt(d);
+    if (tl.lane == 0) { s.dinv[k] = inv; s.L[k * kLD + k] = d * inv; }   // L_kk = sqrt(d): read by J^T f = L z only
     for (int i = k + 1 + tl.lane; i < n; i += LANES) {
-      const T lik = s.L[i * kLD + k];
-      for (int j = k + 1; j <= i; j++) s.L[i * kLD + j] -= lik * s.L[j * kLD + k];
+      T v = s.M[i * kLD + k];
+      for (int j = 0; j < k; j++) v -= s.L[i * kLD + j] * s.L[k * kLD + j];
+      s.L[i * kLD + k] = v * inv;
     }
     tl.sync();
   }
@@ -641,6 +639,102 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
   // (identically in every lane) and publishes the change to all rows
   const T scale = (T)1 / (m.meaninertia * (T)(nv > 1 ? nv : 1));
   int iter = 0;
+#if defined(__CUDACC__)
+  if constexpr (LANES == 32) {
+    // One warp per env: the residuals and forces live in REGISTERS of the lanes that own the rows (lane l owns rows l and
+    // l + 32), a block's residual / old force is a warp shuffle from its owner, the publish is one FMA per owned row on
+    // registers -- no shared-memory traffic for acc / f and no barrier inside the sweep.  Same arithmetic as the general
+    // path below (tests/test_gpu_tree.py runs the fp64 parity cases on 8, 16 and 32 lanes).
+    const int q0 = tl.lane, q1 = tl.lane + 32;
+    const int rb0 = q0 * (q0 + 1) / 2, rb1 = q1 * (q1 + 1) / 2;
+    const bool own0 = q0 < nefc, own1 = q1 < nefc;
+    T acc0 = own0 ? s.r_acc[q0] : (T)0, acc1 = own1 ? s.r_acc[q1] : (T)0;
+    T fr0 = own0 ? s.r_f[q0] : (T)0, fr1 = own1 ? s.r_f[q1] : (T)0;
+#define TREE_BCAST(a0, a1, row) __shfl_sync(0xffffffffu, (row) < 32 ? (a0) : (a1), (row) & 31)
+#define TREE_AIDX(rb, q, row, ib) ((q) >= (row) ? (rb) + (row) : (ib) + (q))
+    while (iter < m.iterations) {
+      T improvement = 0;
+      for (int i = 0; i < nefc;) {
+        const int type = s.r_type[i];
+        const int dim = type == kRowContact ? s.c_dim[s.r_id[i]] : 1;
+        const int ib = i * (i + 1) / 2, di = ib + i;
+        if (dim == 1) {
+          const T res = TREE_BCAST(acc0, acc1, i), old = TREE_BCAST(fr0, fr1, i), aii = s.Am[di];
+          T fn = old - res / aii;
+          if (type != kRowEq && fn < 0) fn = 0;
+          T d0 = fn - old;
+          T change = (T)0.5 * d0 * d0 * aii + d0 * res;
+          if (change > (T)1e-10) { d0 = 0; change = 0; }
+          improvement -= change;
+          if (d0 != 0) {
+            if (q0 == i) fr0 = old + d0;
+            if (q1 == i) fr1 = old + d0;
+            if (own0) acc0 += s.Am[TREE_AIDX(rb0, q0, i, ib)] * d0;
+            if (own1) acc1 += s.Am[TREE_AIDX(rb1, q1, i, ib)] * d0;
+          }
+          i += 1;
+          continue;
+        }
+        const int ib1 = ib + i + 1, ib2 = ib1 + i + 2;        // packed starts of rows i + 1, i + 2
+        const int d1 = di + i + 1, d2 = d1 + i + 2;
+        const T a00 = s.Am[di], a10 = s.Am[d1], a11 = s.Am[d1 + 1], a20 = s.Am[d2], a21 = s.Am[d2 + 1], a22 = s.Am[d2 + 2];
+        const T r0 = TREE_BCAST(acc0, acc1, i), r1 = TREE_BCAST(acc0, acc1, i + 1), r2 = TREE_BCAST(acc0, acc1, i + 2);
+        const T o0 = TREE_BCAST(fr0, fr1, i), o1 = TREE_BCAST(fr0, fr1, i + 1), o2 = TREE_BCAST(fr0, fr1, i + 2);
+        T f0 = o0, f1 = o1, f2 = o2;
+        const T* frc = m.pair_friction[s.c_pair[s.r_id[i]]];
+        const T mu2[2] = {frc[0], frc[0]};
+        if (f0 < (T)kMinVal) {
+          f0 -= r0 / a00;
+          if (f0 < 0) f0 = 0;
+          f1 = f2 = 0;
+        } else {
+          const T v0 = a00 * f0 + a10 * f1 + a20 * f2, v1 = a10 * f0 + a11 * f1 + a21 * f2, v2 = a20 * f0 + a21 * f1 + a22 * f2;
+          const T denom = f0 * v0 + f1 * v1 + f2 * v2;
+          if (denom >= (T)kMinVal) {
+            T x = -(f0 * r0 + f1 * r1 + f2 * r2) / denom;
+            if (f0 + x * f0 < 0) x = -1;
+            const T g0 = f0, g1 = f1, g2 = f2;
+            f0 += x * g0; f1 += x * g1; f2 += x * g2;
+          }
+        }
+        if (f0 < (T)kMinVal) f1 = f2 = 0;
+        else {
+          const T Ac[4] = {a11, a21, a21, a22};
+          const T bc[2] = {r1 - a11 * o1 - a21 * o2 + a10 * (f0 - o0), r2 - a21 * o1 - a22 * o2 + a20 * (f0 - o0)};
+          T v[2];
+          const int active = qcqp2(v, Ac, bc, mu2, f0);
+          if (active) {
+            T sc = v[0] * v[0] / (mu2[0] * mu2[0]) + v[1] * v[1] / (mu2[1] * mu2[1]);
+            sc = sqrt(f0 * f0 / fmax((T)kMinVal, sc));
+            v[0] *= sc; v[1] *= sc;
+          }
+          f1 = v[0]; f2 = v[1];
+        }
+        T e0 = f0 - o0, e1 = f1 - o1, e2 = f2 - o2;
+        T change = (T)0.5 * (e0 * (a00 * e0 + a10 * e1 + a20 * e2) + e1 * (a10 * e0 + a11 * e1 + a21 * e2) + e2 * (a20 * e0 + a21 * e1 + a22 * e2)) +
+                   e0 * r0 + e1 * r1 + e2 * r2;
+        if (change > (T)1e-10) { e0 = e1 = e2 = 0; change = 0; }
+        improvement -= change;
+        if (e0 != 0 || e1 != 0 || e2 != 0) {
+          if (q0 == i) fr0 = o0 + e0; else if (q0 == i + 1) fr0 = o1 + e1; else if (q0 == i + 2) fr0 = o2 + e2;
+          if (q1 == i) fr1 = o0 + e0; else if (q1 == i + 1) fr1 = o1 + e1; else if (q1 == i + 2) fr1 = o2 + e2;
+          if (own0)
+            acc0 += s.Am[TREE_AIDX(rb0, q0, i, ib)] * e0 + s.Am[TREE_AIDX(rb0, q0, i + 1, ib1)] * e1 + s.Am[TREE_AIDX(rb0, q0, i + 2, ib2)] * e2;
+          if (own1)
+            acc1 += s.Am[TREE_AIDX(rb1, q1, i, ib)] * e0 + s.Am[TREE_AIDX(rb1, q1, i + 1, ib1)] * e1 + s.Am[TREE_AIDX(rb1, q1, i + 2, ib2)] * e2;
+        }
+        i += 3;
+      }
+      iter++;
+      if (improvement * scale < m.tolerance) break;
+    }
+#undef TREE_BCAST
+#undef TREE_AIDX
+    if (own0) s.r_f[q0] = fr0;
+    if (own1) s.r_f[q1] = fr1;
+    tl.sync();
+  } else
+#endif
   while (iter < m.iterations) {
     T improvement = 0;
     for (int i = 0; i < nefc;) {

@@ -36,17 +36,11 @@ struct TreeStepArgs {
 
 template <typename T, int LANES>
 __global__ void __launch_bounds__(kTreeMaxBlock)
-k_tree_step(const TreeModel<T>* __restrict__ gm, const TreeBatchView<T> v, const T* __restrict__ action, int n_sub, T z_done,
+k_tree_step(const __grid_constant__ TreeModel<T> m, const TreeBatchView<T> v, const T* __restrict__ action, int n_sub, T z_done,
             int auto_reset, uint8_t* __restrict__ done, const T* __restrict__ reset_q, const T* __restrict__ reset_qd) {
-  __shared__ TreeModel<T> m;
+  // the model (5.9 KB in fp32) is a __grid_constant__ kernel parameter: it lives in the constant bank, is read with
+  // tile-uniform addresses, and costs no shared memory (shared memory is what bounds the resident envs per SM)
   extern __shared__ __align__(16) unsigned char tree_smem[];
-  {  // the model block, once per CTA
-    const int words = (int)(sizeof(TreeModel<T>) / 4);
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(gm);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&m);
-    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
-  }
-  __syncthreads();
   const Tile<LANES> tl = Tile<LANES>::make();
   const int tile_in_block = (int)threadIdx.x / LANES, tiles_per_block = (int)blockDim.x / LANES;
   const int e = (int)blockIdx.x * tiles_per_block + tile_in_block;
@@ -105,14 +99,14 @@ __global__ void k_tree_set_all(TreeBatchView<T> v, int nq, int nv, const T* __re
 
 template <typename T>
 struct TreeLaunch {
-  static cudaError_t step(const TreeModel<T>* dm, const TreeBatchView<T>& v, const TreeStepArgs& a, int lanes, cudaStream_t s);
+  static cudaError_t step(const TreeModel<T>& m, const TreeBatchView<T>& v, const TreeStepArgs& a, int lanes, cudaStream_t s);
   static cudaError_t set_all(const TreeBatchView<T>& v, int nq, int nv, const T* q, const T* qd, const uint8_t* mask, cudaStream_t s);
 };
 
 template <typename T, int LANES>
-inline cudaError_t launch_tree_step(const TreeModel<T>* dm, const TreeBatchView<T>& v, const TreeStepArgs& a, cudaStream_t s) {
-  // Envs (tiles) per CTA: shared memory is the resource (one Scratch block per env + one model copy per CTA).  Default:
-  // two resident CTAs per SM, each with as many tiles as fit; CASSIE3D_TILES overrides.  Whole warps only.
+inline cudaError_t launch_tree_step(const TreeModel<T>& m, const TreeBatchView<T>& v, const TreeStepArgs& a, cudaStream_t s) {
+  // Envs (tiles) per CTA: shared memory is the resource (one Scratch block per env).  Default: two tiles per CTA (small
+  // CTAs backfill best: profiles/r2t_lanes.txt); CASSIE3D_TILES overrides.  Whole warps only.
   static int tiles = 0;
   if (tiles == 0) {
     int dev = 0, smem_sm = 0, smem_blk = 0;
@@ -120,15 +114,15 @@ inline cudaError_t launch_tree_step(const TreeModel<T>* dm, const TreeBatchView<
     cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const int per_warp = 32 / LANES;
-    const int fixed = (int)sizeof(TreeModel<T>) + 1024;            // static model copy + the per-CTA reservation
-    int t = (smem_sm / 2 - fixed) / (int)sizeof(Scratch<T>);
+    int t = 2;
+    (void)smem_sm;
     if (const char* e = getenv("CASSIE3D_TILES")) t = atoi(e);
-    const int cap_blk = (smem_blk - (int)sizeof(TreeModel<T>)) / (int)sizeof(Scratch<T>), cap_thr = kTreeMaxBlock / LANES;
+    const int cap_blk = smem_blk / (int)sizeof(Scratch<T>), cap_thr = kTreeMaxBlock / LANES;
     if (t > cap_blk) t = cap_blk;
     if (t > cap_thr) t = cap_thr;
     t = t / per_warp * per_warp;
     if (t < per_warp) t = per_warp;
-    if ((size_t)t * sizeof(Scratch<T>) + sizeof(TreeModel<T>) > (size_t)smem_blk) return cudaErrorInvalidConfiguration;
+    if ((size_t)t * sizeof(Scratch<T>) > (size_t)smem_blk) return cudaErrorInvalidConfiguration;
     cudaFuncSetAttribute(k_tree_step<T, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)t * sizeof(Scratch<T>)));
     cudaFuncSetAttribute(k_tree_step<T, LANES>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     tiles = t;
@@ -136,7 +130,7 @@ inline cudaError_t launch_tree_step(const TreeModel<T>* dm, const TreeBatchView<
   const int block = tiles * LANES;
   const size_t dyn = (size_t)tiles * sizeof(Scratch<T>);
   const unsigned grid = (unsigned)((v.n + tiles - 1) / tiles);
-  k_tree_step<T, LANES><<<grid, block, dyn, s>>>(dm, v, (const T*)a.action, a.n_sub, (T)a.z_done, a.auto_reset, a.done,
+  k_tree_step<T, LANES><<<grid, block, dyn, s>>>(m, v, (const T*)a.action, a.n_sub, (T)a.z_done, a.auto_reset, a.done,
                                                    (const T*)a.reset_q, (const T*)a.reset_qd);
   count_launch();
   return cudaGetLastError();
@@ -144,7 +138,7 @@ inline cudaError_t launch_tree_step(const TreeModel<T>* dm, const TreeBatchView<
 
 #define CASSIE_TREE_INSTANTIATE(T)                                                                                         \
   template <>                                                                                                              \
-  cudaError_t TreeLaunch<T>::step(const TreeModel<T>* dm, const TreeBatchView<T>& v, const TreeStepArgs& a, int lanes,     \
+  cudaError_t TreeLaunch<T>::step(const TreeModel<T>& dm, const TreeBatchView<T>& v, const TreeStepArgs& a, int lanes,     \
                                   cudaStream_t s) {                                                                        \
     if (lanes == 8) return launch_tree_step<T, 8>(dm, v, a, s);                                                            \
     if (lanes == 16) return launch_tree_step<T, 16>(dm, v, a, s);                                                          \
