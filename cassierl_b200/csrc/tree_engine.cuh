@@ -623,6 +623,7 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
   tl.sync();
   T cost = 0;
   for (int r = tl.lane; r < nefc; r += LANES) {
+    s.r_pos[r] = (T)1 / s.Am[r * (r + 1) / 2 + r];        // 1 / A_rr for the scalar-row updates (jar is consumed)
     T v = 0;
     for (int c = 0; c < nefc; c++) v += s.Am[tri(r, c)] * s.r_f[c];
     s.r_acc[r] = v;
@@ -660,7 +661,7 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
         const int ib = i * (i + 1) / 2, di = ib + i;
         if (dim == 1) {
           const T res = TREE_BCAST(acc0, acc1, i), old = TREE_BCAST(fr0, fr1, i), aii = s.Am[di];
-          T fn = old - res / aii;
+          T fn = old - res * s.r_pos[i];
           if (type != kRowEq && fn < 0) fn = 0;
           T d0 = fn - old;
           T change = (T)0.5 * d0 * d0 * aii + d0 * res;
@@ -744,7 +745,7 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
       if (dim == 1) {
         // ---- scalar row: connect, joint limit, frictionless contact
         const T res = s.r_acc[i], old = s.r_f[i], aii = s.Am[di];
-        T fn = old - res / aii;
+        T fn = old - res * s.r_pos[i];
         if (type != kRowEq && fn < 0) fn = 0;
         T d0 = fn - old;
         T change = (T)0.5 * d0 * d0 * aii + d0 * res;      // costChange: revert an update that raises the dual cost

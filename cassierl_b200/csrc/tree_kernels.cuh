@@ -37,14 +37,16 @@ struct TreeStepArgs {
 template <typename T, int LANES>
 __global__ void __launch_bounds__(kTreeMaxBlock)
 k_tree_step(const __grid_constant__ TreeModel<T> m, const TreeBatchView<T> v, const T* __restrict__ action, int n_sub, T z_done,
-            int auto_reset, uint8_t* __restrict__ done, const T* __restrict__ reset_q, const T* __restrict__ reset_qd) {
+            int auto_reset, uint8_t* __restrict__ done, const T* __restrict__ reset_q, const T* __restrict__ reset_qd,
+            int step_barrier) {
   // the model (5.9 KB in fp32) is a __grid_constant__ kernel parameter: it lives in the constant bank, is read with
   // tile-uniform addresses, and costs no shared memory (shared memory is what bounds the resident envs per SM)
   extern __shared__ __align__(16) unsigned char tree_smem[];
   const Tile<LANES> tl = Tile<LANES>::make();
   const int tile_in_block = (int)threadIdx.x / LANES, tiles_per_block = (int)blockDim.x / LANES;
-  const int e = (int)blockIdx.x * tiles_per_block + tile_in_block;
-  if (e >= v.n) return;                       // whole tiles leave together; no block-wide barrier follows
+  const int e_raw = (int)blockIdx.x * tiles_per_block + tile_in_block;
+  const bool active = e_raw < v.n;           // surplus tiles shadow the last env (they take part in the CTA barriers) and store nothing
+  const int e = active ? e_raw : v.n - 1;
   Scratch<T>& s = *reinterpret_cast<Scratch<T>*>(tree_smem + (size_t)tile_in_block * sizeof(Scratch<T>));
   const int nq = m.nq, nv = m.nv, nu = m.nu;
   const T* gq = v.qpos + (size_t)e * nq;
@@ -57,7 +59,12 @@ k_tree_step(const __grid_constant__ TreeModel<T> m, const TreeBatchView<T> v, co
   if (tl.lane == 0) s.n_dropped = 0;
   tl.sync();
   TreeStats st = {0, 0, 0, 0};
-  for (int k = 0; k < n_sub; k++) tree_step(tl, m, s, s.ctrl, &st);
+  for (int k = 0; k < n_sub; k++) {
+    // optional lock step of the CTA's tiles: the once-per-step code is ~10 k straight-line instructions, and tiles that
+    // run through it together share the instruction-cache fills (CASSIE3D_STEP_BARRIER, profiles/r2v_*)
+    if (step_barrier) __syncthreads();
+    tree_step(tl, m, s, s.ctrl, &st);
+  }
   // termination (every lane evaluates it on the shared state) and auto-reset
   bool bad = false;
   for (int i = 0; i < nq; i++) bad = bad || !isfinite(s.q[i]);
@@ -71,6 +78,7 @@ k_tree_step(const __grid_constant__ TreeModel<T> m, const TreeBatchView<T> v, co
     for (int d = tl.lane; d < nv; d += LANES) { s.qd[d] = reset_qd[m.user_dof[d]]; s.warm[d] = 0; }
     tl.sync();
   }
+  if (!active) return;
   T* oq = v.qpos + (size_t)e * nq;
   T* ov = v.qvel + (size_t)e * nv;
   T* ow = v.warm + (size_t)e * nv;
@@ -130,8 +138,9 @@ inline cudaError_t launch_tree_step(const TreeModel<T>& m, const TreeBatchView<T
   const int block = tiles * LANES;
   const size_t dyn = (size_t)tiles * sizeof(Scratch<T>);
   const unsigned grid = (unsigned)((v.n + tiles - 1) / tiles);
+  static const int step_barrier = [] { const char* e = getenv("CASSIE3D_STEP_BARRIER"); return e ? atoi(e) : 0; }();
   k_tree_step<T, LANES><<<grid, block, dyn, s>>>(m, v, (const T*)a.action, a.n_sub, (T)a.z_done, a.auto_reset, a.done,
-                                                   (const T*)a.reset_q, (const T*)a.reset_qd);
+                                                   (const T*)a.reset_q, (const T*)a.reset_qd, step_barrier);
   count_launch();
   return cudaGetLastError();
 }
