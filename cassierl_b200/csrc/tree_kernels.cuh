@@ -60,8 +60,8 @@ k_tree_step(const __grid_constant__ TreeModel<T> m, const TreeBatchView<T> v, co
   tl.sync();
   TreeStats st = {0, 0, 0, 0};
   for (int k = 0; k < n_sub; k++) {
-    // optional lock step of the CTA's tiles: the once-per-step code is ~10 k straight-line instructions, and tiles that
-    // run through it together share the instruction-cache fills (CASSIE3D_STEP_BARRIER, profiles/r2v_*)
+    // lock step of the CTA's tiles: the once-per-step code is ~10 k straight-line instructions, and tiles that run through
+    // it together share the instruction-cache fills (+15 %, profiles/r2v_sweep.txt; CASSIE3D_STEP_BARRIER=0 turns it off)
     if (step_barrier) __syncthreads();
     tree_step(tl, m, s, s.ctrl, &st);
   }
@@ -138,7 +138,7 @@ inline cudaError_t launch_tree_step(const TreeModel<T>& m, const TreeBatchView<T
   const int block = tiles * LANES;
   const size_t dyn = (size_t)tiles * sizeof(Scratch<T>);
   const unsigned grid = (unsigned)((v.n + tiles - 1) / tiles);
-  static const int step_barrier = [] { const char* e = getenv("CASSIE3D_STEP_BARRIER"); return e ? atoi(e) : 0; }();
+  static const int step_barrier = [] { const char* e = getenv("CASSIE3D_STEP_BARRIER"); return e ? atoi(e) : 1; }();
   k_tree_step<T, LANES><<<grid, block, dyn, s>>>(m, v, (const T*)a.action, a.n_sub, (T)a.z_done, a.auto_reset, a.done,
                                                    (const T*)a.reset_q, (const T*)a.reset_qd, step_barrier);
   count_launch();
