@@ -69,23 +69,31 @@ struct Scratch {
   // kinematics about the base position, world axes
   T xpos[kMaxLinks][3], xmat[kMaxLinks][9];
   T S[kMaxDof][6];
-  T V[kMaxLinks][6], A[kMaxLinks][6];
+  // link velocities, velocity-product accelerations and RNE forces are dead once the bias is formed; the per-row vectors
+  // of the constraint solve are born later: they share storage
+  union {
+    struct { T V[kMaxLinks][6], A[kMaxLinks][6], F[kMaxLinks][6]; };
+    struct { T r_pos[kMaxRows], r_R[kMaxRows], r_aref[kMaxRows], r_b[kMaxRows], r_f[kMaxRows]; };
+  };
+  T r_acc[kMaxRows];
   T Ic[kMaxLinks][10];                 // mass, h = m c (3), inertia about the origin xx yy zz xy xz yz
-  T F[kMaxLinks][6];
   T gw[kMaxGeoms][6];                  // geom points in the world frame (relative to the base)
-  T M[kMaxDof * kLD], L[kMaxDof * kLD], dinv[kMaxDof];
+  // ONE square array for the mass matrix and its factor: strict upper triangle = M (symmetric), lower triangle incl. the
+  // diagonal = L of the current Cholesky factorisation, Mdiag = diagonal of M
+  T L[kMaxDof * kLD], Mdiag[kMaxDof], dinv[kMaxDof];
   T qfrc[kMaxDof], qacc_s[kMaxDof], qacc[kMaxDof], qfc[kMaxDof], tmp[kMaxDof];
   // contacts
   int ncon, nefc, n_dropped, sweeps;
-  int slot_on[2 * kMaxPairs];
+  unsigned char slot_on[2 * kMaxPairs];
   int c_pair[kMaxCon], c_end[kMaxCon], c_dim[kMaxCon];
   T c_dist[kMaxCon], c_pos[kMaxCon][3], c_frame[kMaxCon][9];
   // constraint rows
-  int r_type[kMaxRows], r_id[kMaxRows], r_sub[kMaxRows];
+  signed char r_type[kMaxRows], r_sub[kMaxRows];
+  short r_id[kMaxRows];
   T J[kMaxRows * kLD];                 // constraint Jacobian, overwritten by Y = L^-1 J^T (row r = y_r^T) before the solve
   T Am[kPackedA];
-  T r_pos[kMaxRows], r_R[kMaxRows], r_aref[kMaxRows], r_b[kMaxRows], r_f[kMaxRows], r_acc[kMaxRows];
 };
+static_assert(5 * kMaxRows <= 3 * kMaxLinks * 6, "the row vectors must fit in the storage of V, A, F");
 
 enum RowType { kRowEq = 0, kRowLimit = 1, kRowContact = 2 };
 constexpr double kMinVal = 1e-15;
@@ -278,10 +286,9 @@ TREE_FN void dynamics(const Tile<LANES>& tl, const TreeModel<T>& m, Scratch<T>& 
     const unsigned anc = m.anc[l];
     for (int a = 0; a < d; a++) {
       const T v = ((anc >> a) & 1u) ? dot6(s.S[a], f6) : (T)0;
-      s.M[d * kLD + a] = v;
-      s.M[a * kLD + d] = v;
+      s.L[a * kLD + d] = v;                      // M lives in the strict upper triangle (a < d)
     }
-    s.M[d * kLD + d] = dot6(s.S[d], f6) + m.armature[d];
+    s.Mdiag[d] = dot6(s.S[d], f6) + m.armature[d];
     s.tmp[d] = dot6(s.S[d], s.F[l]);
   }
   tl.sync();
@@ -293,12 +300,12 @@ TREE_FN void dynamics(const Tile<LANES>& tl, const TreeModel<T>& m, Scratch<T>& 
 template <int LANES, typename T>
 TREE_FN void cholesky(const Tile<LANES>& tl, int n, Scratch<T>& s, const T* add, T scale) {
   for (int k = 0; k < n; k++) {
-    T d = s.M[k * kLD + k] + (add ? scale * add[k] : (T)0);
+    T d = s.Mdiag[k] + (add ? scale * add[k] : (T)0);
     for (int j = 0; j < k; j++) { const T l = s.L[k * kLD + j]; d -= l * l; }
     const T inv = (T)1 / sqrt(d);
     if (tl.lane == 0) { s.dinv[k] = inv; s.L[k * kLD + k] = d * inv; }   // L_kk = sqrt(d): read by J^T f = L z only
     for (int i = k + 1 + tl.lane; i < n; i += LANES) {
-      T v = s.M[i * kLD + k];
+      T v = s.L[k * kLD + i];                      // M[i][k] = M[k][i], upper triangle
       for (int j = 0; j < k; j++) v -= s.L[i * kLD + j] * s.L[k * kLD + j];
       s.L[i * kLD + k] = v * inv;
     }

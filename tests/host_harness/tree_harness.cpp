@@ -98,7 +98,7 @@ void th_dynamics(const double* q, const double* qd, double* M, double* bias) {
   dynamics(tl, g_m64, s);
   for (int i = 0; i < g_m64.nv; i++) {
     bias[ud[i]] = s.tmp[i];
-    for (int j = 0; j < g_m64.nv; j++) M[ud[i] * g_m64.nv + ud[j]] = s.M[i * kLD + j];
+    for (int j = 0; j < g_m64.nv; j++) M[ud[i] * g_m64.nv + ud[j]] = i == j ? s.Mdiag[i] : (i < j ? s.L[i * kLD + j] : s.L[j * kLD + i]);
   }
 }
 // constraint rows at (q, qd) in user dof order: returns nefc; J [nefc x nv], pos, R, aref, type, id
