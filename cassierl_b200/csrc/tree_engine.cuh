@@ -648,18 +648,31 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
   const T scale = (T)1 / (m.meaninertia * (T)(nv > 1 ? nv : 1));
   int iter = 0;
 #if defined(__CUDACC__)
-  if constexpr (LANES == 32) {
-    // One warp per env: the residuals and forces live in REGISTERS of the lanes that own the rows (lane l owns rows l and
-    // l + 32), a block's residual / old force is a warp shuffle from its owner, the publish is one FMA per owned row on
-    // registers -- no shared-memory traffic for acc / f and no barrier inside the sweep.  Same arithmetic as the general
-    // path below (tests/test_gpu_tree.py runs the fp64 parity cases on 8, 16 and 32 lanes).
-    const int q0 = tl.lane, q1 = tl.lane + 32;
-    const int rb0 = q0 * (q0 + 1) / 2, rb1 = q1 * (q1 + 1) / 2;
-    const bool own0 = q0 < nefc, own1 = q1 < nefc;
-    T acc0 = own0 ? s.r_acc[q0] : (T)0, acc1 = own1 ? s.r_acc[q1] : (T)0;
-    T fr0 = own0 ? s.r_f[q0] : (T)0, fr1 = own1 ? s.r_f[q1] : (T)0;
-#define TREE_BCAST(a0, a1, row) __shfl_sync(0xffffffffu, (row) < 32 ? (a0) : (a1), (row) & 31)
-#define TREE_AIDX(rb, q, row, ib) ((q) >= (row) ? (rb) + (row) : (ib) + (q))
+  if constexpr (LANES >= 8) {
+    // The residuals and forces live in REGISTERS of the lanes that own the rows (lane l of the tile owns rows l, l + LANES,
+    // ...: K slots), a block's residual / old force is a tile shuffle from its owner, the publish is one FMA per owned row
+    // on registers -- no shared-memory traffic for acc / f and no barrier inside the sweep.  Same arithmetic as the general
+    // path below (tests/test_gpu_tree.py runs the fp64 parity cases on 8, 16 and 32 lanes; the CPU harness runs the
+    // general path).
+    constexpr int K = (kMaxRows + LANES - 1) / LANES;
+    T acc[K], fr[K];
+    int rb[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const int q = tl.lane + k * LANES;
+      rb[k] = q * (q + 1) / 2;
+      acc[k] = q < nefc ? s.r_acc[q] : (T)0;
+      fr[k] = q < nefc ? s.r_f[q] : (T)0;
+    }
+    // value of row `row` from its owner
+    auto bcast = [&](const T (&a)[K], int row) -> T {
+      T sel = a[0];
+#pragma unroll
+      for (int k = 1; k < K; k++) sel = row >= k * LANES ? a[k] : sel;
+      return __shfl_sync(tl.mask, sel, row & (LANES - 1), LANES);
+    };
+    // packed index of A[row][q] given the packed starts of rows q (rbq) and row (ib)
+#define TREE_AIDX(rbq, q, row, ib) ((q) >= (row) ? (rbq) + (row) : (ib) + (q))
     while (iter < m.iterations) {
       T improvement = 0;
       for (int i = 0; i < nefc;) {
@@ -667,7 +680,7 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
         const int dim = type == kRowContact ? s.c_dim[s.r_id[i]] : 1;
         const int ib = i * (i + 1) / 2, di = ib + i;
         if (dim == 1) {
-          const T res = TREE_BCAST(acc0, acc1, i), old = TREE_BCAST(fr0, fr1, i), aii = s.Am[di];
+          const T res = bcast(acc, i), old = bcast(fr, i), aii = s.Am[di];
           T fn = old - res * s.r_pos[i];
           if (type != kRowEq && fn < 0) fn = 0;
           T d0 = fn - old;
@@ -675,10 +688,12 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
           if (change > (T)1e-10) { d0 = 0; change = 0; }
           improvement -= change;
           if (d0 != 0) {
-            if (q0 == i) fr0 = old + d0;
-            if (q1 == i) fr1 = old + d0;
-            if (own0) acc0 += s.Am[TREE_AIDX(rb0, q0, i, ib)] * d0;
-            if (own1) acc1 += s.Am[TREE_AIDX(rb1, q1, i, ib)] * d0;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+              const int q = tl.lane + k * LANES;
+              if (q == i) fr[k] = old + d0;
+              if (q < nefc) acc[k] += s.Am[TREE_AIDX(rb[k], q, i, ib)] * d0;
+            }
           }
           i += 1;
           continue;
@@ -686,8 +701,8 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
         const int ib1 = ib + i + 1, ib2 = ib1 + i + 2;        // packed starts of rows i + 1, i + 2
         const int d1 = di + i + 1, d2 = d1 + i + 2;
         const T a00 = s.Am[di], a10 = s.Am[d1], a11 = s.Am[d1 + 1], a20 = s.Am[d2], a21 = s.Am[d2 + 1], a22 = s.Am[d2 + 2];
-        const T r0 = TREE_BCAST(acc0, acc1, i), r1 = TREE_BCAST(acc0, acc1, i + 1), r2 = TREE_BCAST(acc0, acc1, i + 2);
-        const T o0 = TREE_BCAST(fr0, fr1, i), o1 = TREE_BCAST(fr0, fr1, i + 1), o2 = TREE_BCAST(fr0, fr1, i + 2);
+        const T r0 = bcast(acc, i), r1 = bcast(acc, i + 1), r2 = bcast(acc, i + 2);
+        const T o0 = bcast(fr, i), o1 = bcast(fr, i + 1), o2 = bcast(fr, i + 2);
         T f0 = o0, f1 = o1, f2 = o2;
         const T* frc = m.pair_friction[s.c_pair[s.r_id[i]]];
         const T mu2[2] = {frc[0], frc[0]};
@@ -724,22 +739,25 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
         if (change > (T)1e-10) { e0 = e1 = e2 = 0; change = 0; }
         improvement -= change;
         if (e0 != 0 || e1 != 0 || e2 != 0) {
-          if (q0 == i) fr0 = o0 + e0; else if (q0 == i + 1) fr0 = o1 + e1; else if (q0 == i + 2) fr0 = o2 + e2;
-          if (q1 == i) fr1 = o0 + e0; else if (q1 == i + 1) fr1 = o1 + e1; else if (q1 == i + 2) fr1 = o2 + e2;
-          if (own0)
-            acc0 += s.Am[TREE_AIDX(rb0, q0, i, ib)] * e0 + s.Am[TREE_AIDX(rb0, q0, i + 1, ib1)] * e1 + s.Am[TREE_AIDX(rb0, q0, i + 2, ib2)] * e2;
-          if (own1)
-            acc1 += s.Am[TREE_AIDX(rb1, q1, i, ib)] * e0 + s.Am[TREE_AIDX(rb1, q1, i + 1, ib1)] * e1 + s.Am[TREE_AIDX(rb1, q1, i + 2, ib2)] * e2;
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            const int q = tl.lane + k * LANES;
+            if (q == i) fr[k] = o0 + e0; else if (q == i + 1) fr[k] = o1 + e1; else if (q == i + 2) fr[k] = o2 + e2;
+            if (q < nefc)
+              acc[k] += s.Am[TREE_AIDX(rb[k], q, i, ib)] * e0 + s.Am[TREE_AIDX(rb[k], q, i + 1, ib1)] * e1 + s.Am[TREE_AIDX(rb[k], q, i + 2, ib2)] * e2;
+          }
         }
         i += 3;
       }
       iter++;
       if (improvement * scale < m.tolerance) break;
     }
-#undef TREE_BCAST
 #undef TREE_AIDX
-    if (own0) s.r_f[q0] = fr0;
-    if (own1) s.r_f[q1] = fr1;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const int q = tl.lane + k * LANES;
+      if (q < nefc) s.r_f[q] = fr[k];
+    }
     tl.sync();
   } else
 #endif
