@@ -149,3 +149,33 @@ def test_tree_step_host_matches_device():
     b2.step_host(ah, qh, vh, dh, n=10)
     assert torch.equal(q1.cpu(), qh) and torch.equal(v1.cpu(), vh)
     b1.close(); b2.close()
+
+
+def test_tree_nan_guard_and_masked_reset():
+    """a non-finite env is reported done = 2 and restarts from the reset state in the same launch (it never poisons its
+    neighbours); ResetAll with a mask touches the flagged envs only"""
+    import torch
+    from cassierl_b200.envs3d import Cassie3dBatch
+    n = 96
+    b = Cassie3dBatch(n, precision=32)
+    rq, rv = b.reset_state()
+    q, v = b.state()
+    q[5, 9] = float("nan"); v[40, 3] = float("inf")
+    b.set_state(q, v)
+    d = b.step(None, n=10, z_done=0.5, auto_reset=True).cpu().numpy()
+    assert d[5] == 2 and d[40] == 2 and (np.delete(d, [5, 40]) == 0).all()
+    q2, v2 = b.state()
+    assert torch.isfinite(q2).all() and torch.isfinite(v2).all()
+    assert np.abs(q2[5].cpu().numpy() - rq).max() < 1e-6 and np.abs(v2[40].cpu().numpy() - rv).max() < 1e-6
+    assert (b.resets().cpu().numpy()[[5, 40]] == 1).all() and b.resets().sum().item() == 2
+    # neighbours of the bad envs moved like everybody else (all envs started from the same pose)
+    assert (q2[6] - q2[7]).abs().max().item() < 1e-6
+    # masked reset
+    b.step(None, n=50)
+    before = b.state()[0].clone()
+    mask = torch.zeros(n, dtype=torch.uint8); mask[::3] = 1
+    b.reset(mask)
+    after = b.state()[0]
+    assert torch.equal(after[1::3], before[1::3]) and torch.equal(after[2::3], before[2::3])
+    assert np.abs(after[::3].cpu().numpy() - rq.astype(np.float32)).max() < 1e-6
+    b.close()
