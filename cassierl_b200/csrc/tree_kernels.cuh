@@ -113,8 +113,9 @@ struct TreeLaunch {
 
 template <typename T, int LANES>
 inline cudaError_t launch_tree_step(const TreeModel<T>& m, const TreeBatchView<T>& v, const TreeStepArgs& a, cudaStream_t s) {
-  // Envs (tiles) per CTA: shared memory is the resource (one Scratch block per env).  Default: two tiles per CTA (small
-  // CTAs backfill best: profiles/r2t_lanes.txt); CASSIE3D_TILES overrides.  Whole warps only.
+  // Envs (tiles) per CTA: shared memory is the resource (one Scratch block per env).  Default: two resident CTAs per SM
+  // with as many tiles each as fit (7 in fp32): the tiles of a CTA run in lock step (k_tree_step) and share their
+  // instruction-cache fills (profiles/r2aa_tree_sweep_v7.txt: 9.3e6 vs 8.3e6 with two tiles); CASSIE3D_TILES overrides.
   static int tiles = 0;
   if (tiles == 0) {
     int dev = 0, smem_sm = 0, smem_blk = 0;
@@ -122,8 +123,7 @@ inline cudaError_t launch_tree_step(const TreeModel<T>& m, const TreeBatchView<T
     cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const int per_warp = 32 / LANES;
-    int t = 2;
-    (void)smem_sm;
+    int t = (smem_sm / 2 - 1024) / (int)sizeof(Scratch<T>);       // two resident CTAs per SM, as many tiles each as fit
     if (const char* e = getenv("CASSIE3D_TILES")) t = atoi(e);
     const int cap_blk = smem_blk / (int)sizeof(Scratch<T>), cap_thr = kTreeMaxBlock / LANES;
     if (t > cap_blk) t = cap_blk;
