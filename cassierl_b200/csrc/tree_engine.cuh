@@ -40,8 +40,13 @@ struct Tile {
 #if defined(__CUDACC__)
   int lane;
   unsigned mask;
+  int cta_phase_sync;     // > 0: the tiles of a CTA also meet at the phase boundaries inside a step (k_tree_step sets it)
+  // CTA-wide rendezvous at a phase boundary of tree_step: every tile of the CTA walks the same phases, so that they
+  // stream through the same code together (instruction-cache sharing)
+  __device__ __forceinline__ void phase() const { if (cta_phase_sync) __syncthreads(); }
   __device__ __forceinline__ static Tile make() {
     Tile t;
+    t.cta_phase_sync = 0;
     const unsigned l = threadIdx.x & 31u;
     t.lane = (int)(l & (unsigned)(LANES - 1));
     t.mask = LANES == 32 ? 0xffffffffu : (((1u << (LANES & 31)) - 1u) << (l & ~(unsigned)(LANES - 1)));
@@ -57,6 +62,7 @@ struct Tile {
   int lane;
   static Tile make() { Tile t; t.lane = 0; return t; }
   void sync() const {}
+  void phase() const {}
   template <typename V> V sum(V v) const { return v; }
 #endif
 };
@@ -81,7 +87,7 @@ struct Scratch {
   // ONE square array for the mass matrix and its factor: strict upper triangle = M (symmetric), lower triangle incl. the
   // diagonal = L of the current Cholesky factorisation, Mdiag = diagonal of M
   T L[kMaxDof * kLD], Mdiag[kMaxDof], dinv[kMaxDof];
-  T qfrc[kMaxDof], qacc_s[kMaxDof], qacc[kMaxDof], qfc[kMaxDof], tmp[kMaxDof];
+  T qfrc[kMaxDof], qacc_s[kMaxDof], qacc[kMaxDof], qfc[kMaxDof], tmp[kMaxDof], wk[kMaxDof];
   // contacts
   int ncon, nefc, n_dropped, sweeps;
   unsigned char slot_on[2 * kMaxPairs];
@@ -295,48 +301,51 @@ TREE_FN void dynamics(const Tile<LANES>& tl, const TreeModel<T>& m, Scratch<T>& 
   tl.sync();
 }
 
-// dense Cholesky of (M + diag(add)) into s.L (lower triangle) and s.dinv = 1 / L_kk.  Left-looking, one row per
-// lane and ONE tile barrier per column: every lane forms the pivot of column k itself (from row k, complete since the
-// previous barrier), then its own entry L[i][k] = (M[i][k] - sum_j L[i][j] L[k][j]) / L[k][k].
+// dense Cholesky of (M + diag(add)) into s.L (lower triangle) and s.dinv = 1 / L_kk.  Left-looking, rows owned by fixed
+// lanes, ONE tile barrier per column: the running diagonal wk[i] = M_ii - sum_{j<k} L_ij^2 is kept by the owner of row i,
+// so the pivot of column k is one shared-memory read; L[i][k] = (M[i][k] - sum_j L[i][j] L[k][j]) / L[k][k].
 template <int LANES, typename T>
 TREE_FN void cholesky(const Tile<LANES>& tl, int n, Scratch<T>& s, const T* add, T scale) {
+  for (int i = tl.lane; i < n; i += LANES) s.wk[i] = s.Mdiag[i] + (add ? scale * add[i] : (T)0);
+  tl.sync();
   for (int k = 0; k < n; k++) {
-    T d = s.Mdiag[k] + (add ? scale * add[k] : (T)0);
-    for (int j = 0; j < k; j++) { const T l = s.L[k * kLD + j]; d -= l * l; }
+    const T d = s.wk[k];
     const T inv = (T)1 / sqrt(d);
     if (tl.lane == 0) { s.dinv[k] = inv; s.L[k * kLD + k] = d * inv; }   // L_kk = sqrt(d): read by J^T f = L z only
-    for (int i = k + 1 + tl.lane; i < n; i += LANES) {
+    for (int i = tl.lane; i < n; i += LANES) {
+      if (i <= k) continue;
       T v = s.L[k * kLD + i];                      // M[i][k] = M[k][i], upper triangle
       for (int j = 0; j < k; j++) v -= s.L[i * kLD + j] * s.L[k * kLD + j];
-      s.L[i * kLD + k] = v * inv;
+      v *= inv;
+      s.L[i * kLD + k] = v;
+      s.wk[i] -= v * v;
     }
     tl.sync();
   }
 }
 
-// x <- L^-T x for one vector in shared memory, cooperative
+// x <- L^-T x for one vector in shared memory, cooperative: the finished entries go to `out` (a different array), so a
+// column needs ONE barrier
 template <int LANES, typename T>
-TREE_FN void backward_one(const Tile<LANES>& tl, int n, const Scratch<T>& s, T* x) {
+TREE_FN void backward_one(const Tile<LANES>& tl, int n, const Scratch<T>& s, T* x, T* out) {
   for (int k = n - 1; k >= 0; k--) {
     const T xk = x[k] * s.dinv[k];
-    tl.sync();
-    if (tl.lane == 0) x[k] = xk;
+    if (tl.lane == 0) out[k] = xk;
     for (int j = tl.lane; j < k; j += LANES) x[j] -= s.L[k * kLD + j] * xk;
     tl.sync();
   }
 }
 
-// x <- (L L^T)^-1 x for one vector in shared memory, cooperative (column sweeps, one FMA per lane and step)
+// x <- (L L^T)^-1 x for one vector in shared memory, cooperative (column sweeps, one FMA per lane and step); s.wk is scratch
 template <int LANES, typename T>
-TREE_FN void solve_one(const Tile<LANES>& tl, int n, const Scratch<T>& s, T* x) {
+TREE_FN void solve_one(const Tile<LANES>& tl, int n, Scratch<T>& s, T* x) {
   for (int k = 0; k < n; k++) {
     const T xk = x[k] * s.dinv[k];
-    tl.sync();
-    if (tl.lane == 0) x[k] = xk;
+    if (tl.lane == 0) s.wk[k] = xk;
     for (int i = k + 1 + tl.lane; i < n; i += LANES) x[i] -= s.L[i * kLD + k] * xk;
     tl.sync();
   }
-  backward_one(tl, n, s, x);
+  backward_one(tl, n, s, s.wk, x);
 }
 
 // one lane, one right-hand side: x <- L^-1 x (forward substitution, serial)
@@ -866,8 +875,8 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
     s.qfc[i] = a;
   }
   tl.sync();
-  backward_one(tl, nv, s, s.qacc);
-  for (int d = tl.lane; d < nv; d += LANES) s.qacc[d] += s.qacc_s[d];
+  backward_one(tl, nv, s, s.qacc, s.wk);
+  for (int d = tl.lane; d < nv; d += LANES) s.qacc[d] = s.qacc_s[d] + s.wk[d];
   tl.sync();
 }
 
@@ -889,13 +898,17 @@ TREE_FN void tree_step(const Tile<LANES>& tl, const TreeModel<T>& m, Scratch<T>&
       s.qfrc[m.act_dof[a]] += m.act_gear[a] * c;
     }
   tl.sync();
+  tl.phase();
   cholesky(tl, nv, s, (const T*)nullptr, (T)0);
   for (int d = tl.lane; d < nv; d += LANES) s.qacc_s[d] = s.qfrc[d];
   tl.sync();
   solve_one(tl, nv, s, s.qacc_s);
+  tl.phase();
   collide(tl, m, s);
   make_rows(tl, m, s);
+  tl.phase();
   solve_constraints(tl, m, s);
+  tl.phase();
   // mj_Euler: (M + h D) qacc' = qfrc_smooth + qfrc_constraint; qvel += h qacc'; qpos integrated with the NEW velocity
   const T h = m.timestep;
   cholesky(tl, nv, s, m.damping, h);

@@ -42,7 +42,8 @@ k_tree_step(const __grid_constant__ TreeModel<T> m, const TreeBatchView<T> v, co
   // the model (5.9 KB in fp32) is a __grid_constant__ kernel parameter: it lives in the constant bank, is read with
   // tile-uniform addresses, and costs no shared memory (shared memory is what bounds the resident envs per SM)
   extern __shared__ __align__(16) unsigned char tree_smem[];
-  const Tile<LANES> tl = Tile<LANES>::make();
+  Tile<LANES> tl = Tile<LANES>::make();
+  tl.cta_phase_sync = step_barrier < 0 ? 1 : 0;     // CASSIE3D_STEP_BARRIER=-1: also at the phase boundaries inside a step
   const int tile_in_block = (int)threadIdx.x / LANES, tiles_per_block = (int)blockDim.x / LANES;
   const int e_raw = (int)blockIdx.x * tiles_per_block + tile_in_block;
   const bool active = e_raw < v.n;           // surplus tiles shadow the last env (they take part in the CTA barriers) and store nothing
@@ -62,7 +63,7 @@ k_tree_step(const __grid_constant__ TreeModel<T> m, const TreeBatchView<T> v, co
   for (int k = 0; k < n_sub; k++) {
     // lock step of the CTA's tiles: the once-per-step code is ~10 k straight-line instructions, and tiles that run through
     // it together share the instruction-cache fills (+15 %, profiles/r2v_sweep.txt; CASSIE3D_STEP_BARRIER=0 turns it off)
-    if (step_barrier) __syncthreads();
+    if (step_barrier < 0 || (step_barrier > 0 && k % step_barrier == 0)) __syncthreads();   // every step_barrier-th simulator step
     tree_step(tl, m, s, s.ctrl, &st);
   }
   // termination (every lane evaluates it on the shared state) and auto-reset
