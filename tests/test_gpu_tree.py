@@ -179,3 +179,33 @@ def test_tree_nan_guard_and_masked_reset():
     assert torch.equal(after[1::3], before[1::3]) and torch.equal(after[2::3], before[2::3])
     assert np.abs(after[::3].cpu().numpy() - rq.astype(np.float32)).max() < 1e-6
     b.close()
+
+
+def test_tree_big_ragged_batch_subset_vs_oracle(oracle, omodel3d):
+    """configs[3]-sized shard with a ragged tail (8192 + 3 envs: the last CTA has idle tiles), every env in its own state:
+    one fp32 step, 24 envs scattered over the grid (first / last CTA, CTA boundaries) checked against the oracle at 1e-5"""
+    import torch
+    from cassierl_b200.envs3d import Cassie3dBatch
+    n = 8192 + 3
+    q0, v0 = _starts(n, seed=11)
+    rng = np.random.default_rng(12)
+    A = rng.uniform(-1, 1, (n, 10)) * TORQUE_HIGH_3D
+    b = Cassie3dBatch(n, precision=32)
+    b.set_state(q0, v0)
+    b.step(torch.tensor(A), n=1)
+    q, v = (x.cpu().numpy().astype(np.float64) for x in b.state())
+    rows = b.stats().cpu().numpy()[:, 0]
+    b.close()
+    idx = np.unique(np.concatenate([[0, 1, 6, 7, 8, 13, 14, 15], rng.integers(16, n - 16, 8), [n - 8, n - 7, n - 4, n - 3, n - 2, n - 1]]))
+    assert np.isfinite(q).all() and np.isfinite(v).all()
+    bad = []
+    for e in idx:
+        d = oracle.Data(omodel3d)
+        d.set_state(q0[e], v0[e])
+        d.step(A[e])
+        qo, vo = d.state()
+        err = max(np.abs(q[e] - qo).max(), np.abs(v[e] - vo).max() / max(1.0, np.abs(vo).max()))
+        if rows[e] == d.efc()["J"].shape[0] and err >= 1e-5:
+            bad.append((int(e), err))
+        assert err < 1e-2, (e, err)
+    assert not bad, bad
