@@ -20,9 +20,11 @@
 #include "tree_model.h"
 
 #if defined(__CUDACC__)
+#define TREE_UNROLL4 _Pragma("unroll 4")
 #define TREE_FN __device__ __forceinline__
 #define TREE_HD __host__ __device__ __forceinline__
 #else
+#define TREE_UNROLL4
 #define TREE_FN inline
 #define TREE_HD inline
 #endif
@@ -315,6 +317,7 @@ TREE_FN void cholesky(const Tile<LANES>& tl, int n, Scratch<T>& s, const T* add,
     for (int i = tl.lane; i < n; i += LANES) {
       if (i <= k) continue;
       T v = s.L[k * kLD + i];                      // M[i][k] = M[k][i], upper triangle
+      TREE_UNROLL4
       for (int j = 0; j < k; j++) v -= s.L[i * kLD + j] * s.L[k * kLD + j];
       v *= inv;
       s.L[i * kLD + k] = v;
@@ -353,6 +356,7 @@ template <typename T>
 TREE_FN void forward_row(int n, const Scratch<T>& s, T* x) {
   for (int i = 0; i < n; i++) {
     T v = x[i];
+    TREE_UNROLL4
     for (int j = 0; j < i; j++) v -= s.L[i * kLD + j] * x[j];
     x[i] = v * s.dinv[i];
   }
@@ -547,6 +551,7 @@ TREE_FN void make_rows(const Tile<LANES>& tl, const TreeModel<T>& m, Scratch<T>&
     if (R < (T)kMinVal) R = (T)kMinVal;
     if (type == kRowContact && sub > 0) R = R / fmax((T)kMinVal, m.impratio);   // tangent rows (friction[0] == friction[1])
     T vel = 0;
+    TREE_UNROLL4
     for (int d = 0; d < nv; d++) vel += Jr[d] * s.qd[d];
     s.r_pos[r] = pos;
     s.r_R[r] = R;
@@ -593,6 +598,7 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
   for (int r = tl.lane; r < nefc; r += LANES) {
     T* Jr = s.J + r * kLD;
     T bsum = 0, wsum = 0;
+    TREE_UNROLL4
     for (int d = 0; d < nv; d++) { bsum += Jr[d] * s.qacc_s[d]; wsum += Jr[d] * s.warm[d]; }
     s.r_b[r] = bsum - s.r_aref[r];
     s.r_pos[r] = wsum - s.r_aref[r];
@@ -605,6 +611,7 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
     for (int c = 0; c <= r; c++) {
       const T* Yc = s.J + c * kLD;
       T v = 0;
+      TREE_UNROLL4
       for (int d = 0; d < nv; d++) v += Yr[d] * Yc[d];
       if (c == r) v += s.r_R[r];
       Ar[c] = v;
@@ -642,6 +649,7 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
   for (int r = tl.lane; r < nefc; r += LANES) {
     s.r_pos[r] = (T)1 / s.Am[r * (r + 1) / 2 + r];        // 1 / A_rr for the scalar-row updates (jar is consumed)
     T v = 0;
+    TREE_UNROLL4
     for (int c = 0; c < nefc; c++) v += s.Am[tri(r, c)] * s.r_f[c];
     s.r_acc[r] = v;
     cost += s.r_f[r] * ((T)0.5 * v + s.r_b[r]);
@@ -865,6 +873,7 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
   // z = Y f ; qfrc_constraint = J^T f = L z ; qacc = qacc_smooth + M^-1 J^T f = qacc_smooth + L^-T z
   for (int d = tl.lane; d < nv; d += LANES) {
     T a = 0;
+    TREE_UNROLL4
     for (int r = 0; r < nefc; r++) a += s.J[r * kLD + d] * s.r_f[r];
     s.qacc[d] = a;
   }
