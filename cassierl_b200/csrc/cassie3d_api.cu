@@ -79,7 +79,8 @@ int setup(Cassie3dBatch* h, TreeBatchView<T>& v) {
   v.n = h->n;
   if (dmalloc(h, (void**)&v.qpos, sizeof(T) * n * m.nq) || dmalloc(h, (void**)&v.qvel, sizeof(T) * n * m.nv) ||
       dmalloc(h, (void**)&v.warm, sizeof(T) * n * m.nv) || dmalloc(h, (void**)&v.stats, sizeof(int32_t) * 4 * n) ||
-      dmalloc(h, (void**)&v.resets, sizeof(int32_t) * n) || dmalloc(h, &h->d_reset_q, sizeof(T) * m.nq) ||
+      dmalloc(h, (void**)&v.resets, sizeof(int32_t) * n) ||
+      dmalloc(h, (void**)&v.order, sizeof(int32_t) * n) || dmalloc(h, (void**)&v.bins, sizeof(int32_t) * 2 * kTreeBins) || dmalloc(h, &h->d_reset_q, sizeof(T) * m.nq) ||
       dmalloc(h, &h->d_reset_qd, sizeof(T) * m.nv) || dmalloc(h, &h->d_action, sizeof(T) * n * m.nu) ||
       dmalloc(h, (void**)&h->d_done, n))
     return -1;

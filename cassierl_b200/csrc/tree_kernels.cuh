@@ -22,7 +22,10 @@ struct TreeBatchView {
   T* warm;        // [n][nv]  qacc_warmstart
   int32_t* stats; // [n][4]: constraint rows, contacts, PGS sweeps of the last step; contacts dropped (cumulative)
   int32_t* resets; // [n] auto-resets so far
+  int32_t* order;  // [n] tile slot -> env: envs binned by the row count of their last step (k_tree_bin_*), or nullptr
+  int32_t* bins;   // [2 * kTreeBins] histogram / cursors of that binning
 };
+constexpr int kTreeBins = 64;
 
 struct TreeStepArgs {
   const void* action;   // real [n][nu], held for n_sub simulator steps; nullptr = zero controls
@@ -47,7 +50,10 @@ k_tree_step(const __grid_constant__ TreeModel<T> m, const TreeBatchView<T> v, co
   const int tile_in_block = (int)threadIdx.x / LANES, tiles_per_block = (int)blockDim.x / LANES;
   const int e_raw = (int)blockIdx.x * tiles_per_block + tile_in_block;
   const bool active = e_raw < v.n;           // surplus tiles shadow the last env (they take part in the CTA barriers) and store nothing
-  const int e = active ? e_raw : v.n - 1;
+  const int slot = active ? e_raw : v.n - 1;
+  // the tiles of a CTA run in lock step, so a CTA is as slow as its env with the most constraint rows: slots are handed
+  // out in the order of the last step's row counts (envs of similar cost share a CTA); results do not depend on it
+  const int e = v.order ? v.order[slot] : slot;
   Scratch<T>& s = *reinterpret_cast<Scratch<T>*>(tree_smem + (size_t)tile_in_block * sizeof(Scratch<T>));
   const int nq = m.nq, nv = m.nv, nu = m.nu;
   const T* gq = v.qpos + (size_t)e * nq;
@@ -96,6 +102,26 @@ k_tree_step(const __grid_constant__ TreeModel<T> m, const TreeBatchView<T> v, co
   }
 }
 
+// ---- binning of the envs by the constraint-row count of their last step (a counting sort in three tiny launches)
+static __global__ void k_tree_bin_hist(int n, const int32_t* __restrict__ stats, int32_t* __restrict__ bins) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  int key = stats[4 * e];
+  key = key < 0 ? 0 : (key >= kTreeBins ? kTreeBins - 1 : key);
+  atomicAdd(&bins[key], 1);
+}
+static __global__ void k_tree_bin_scan(int32_t* __restrict__ bins) {   // one thread: exclusive prefix into the cursors, histogram cleared
+  int acc = 0;
+  for (int k = 0; k < kTreeBins; k++) { bins[kTreeBins + k] = acc; acc += bins[k]; bins[k] = 0; }
+}
+static __global__ void k_tree_bin_scatter(int n, const int32_t* __restrict__ stats, int32_t* __restrict__ bins, int32_t* __restrict__ order) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  int key = stats[4 * e];
+  key = key < 0 ? 0 : (key >= kTreeBins ? kTreeBins - 1 : key);
+  order[atomicAdd(&bins[kTreeBins + key], 1)] = e;
+}
+
 // qpos / qvel of selected envs <- one state (reset); warm start cleared
 template <typename T>
 __global__ void k_tree_set_all(TreeBatchView<T> v, int nq, int nv, const T* __restrict__ q, const T* __restrict__ qd,
@@ -140,7 +166,16 @@ inline cudaError_t launch_tree_step(const TreeModel<T>& m, const TreeBatchView<T
   const size_t dyn = (size_t)tiles * sizeof(Scratch<T>);
   const unsigned grid = (unsigned)((v.n + tiles - 1) / tiles);
   static const int step_barrier = [] { const char* e = getenv("CASSIE3D_STEP_BARRIER"); return e ? atoi(e) : 1; }();
-  k_tree_step<T, LANES><<<grid, block, dyn, s>>>(m, v, (const T*)a.action, a.n_sub, (T)a.z_done, a.auto_reset, a.done,
+  static const int sort_envs = [] { const char* e = getenv("CASSIE3D_SORT"); return e ? atoi(e) : 0; }();   // measured +1 %: off by default (profiles/r2ac_tree_lockstep.txt)
+  TreeBatchView<T> vv = v;
+  if (sort_envs && step_barrier && v.order && v.bins && tiles > 1) {
+    k_tree_bin_hist<<<(v.n + 255) / 256, 256, 0, s>>>(v.n, v.stats, v.bins);
+    k_tree_bin_scan<<<1, 1, 0, s>>>(v.bins);
+    k_tree_bin_scatter<<<(v.n + 255) / 256, 256, 0, s>>>(v.n, v.stats, v.bins, v.order);
+    count_launch(); count_launch(); count_launch();
+  } else
+    vv.order = nullptr;
+  k_tree_step<T, LANES><<<grid, block, dyn, s>>>(m, vv, (const T*)a.action, a.n_sub, (T)a.z_done, a.auto_reset, a.done,
                                                    (const T*)a.reset_q, (const T*)a.reset_qd, step_barrier);
   count_launch();
   return cudaGetLastError();
