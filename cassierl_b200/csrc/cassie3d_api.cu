@@ -80,7 +80,8 @@ int setup(Cassie3dBatch* h, TreeBatchView<T>& v) {
   if (dmalloc(h, (void**)&v.qpos, sizeof(T) * n * m.nq) || dmalloc(h, (void**)&v.qvel, sizeof(T) * n * m.nv) ||
       dmalloc(h, (void**)&v.warm, sizeof(T) * n * m.nv) || dmalloc(h, (void**)&v.stats, sizeof(int32_t) * 4 * n) ||
       dmalloc(h, (void**)&v.resets, sizeof(int32_t) * n) ||
-      dmalloc(h, (void**)&v.order, sizeof(int32_t) * n) || dmalloc(h, (void**)&v.bins, sizeof(int32_t) * 2 * kTreeBins) || dmalloc(h, &h->d_reset_q, sizeof(T) * m.nq) ||
+      dmalloc(h, (void**)&v.order, sizeof(int32_t) * n) || dmalloc(h, (void**)&v.bins, sizeof(int32_t) * 2 * kTreeBins) ||
+      dmalloc(h, (void**)&v.resume, sizeof(int32_t) * n) || dmalloc(h, &h->d_reset_q, sizeof(T) * m.nq) ||
       dmalloc(h, &h->d_reset_qd, sizeof(T) * m.nv) || dmalloc(h, &h->d_action, sizeof(T) * n * m.nu) ||
       dmalloc(h, (void**)&h->d_done, n))
     return -1;
@@ -167,7 +168,7 @@ void Cassie3dBatchDestroy(Cassie3dBatch* h) {
 int Cassie3dBatchSizes(Cassie3dBatch* h, int32_t* out) {
   if (!h || !out) return fail3("null argument");
   out[0] = h->model.nq; out[1] = h->model.nv; out[2] = h->model.nu; out[3] = tree::kMaxRows; out[4] = tree::kMaxCon;
-  out[5] = (int32_t)(h->precision == 64 ? sizeof(Scratch<double>) : sizeof(Scratch<float>));
+  out[5] = (int32_t)(h->precision == 64 ? sizeof(Scratch<double, tree::kFastRows, tree::kFastCon>) : sizeof(Scratch<float, tree::kFastRows, tree::kFastCon>));
   return 0;
 }
 

@@ -33,7 +33,6 @@ namespace cassie {
 namespace tree {
 
 constexpr int kLD = kMaxDof + 1;       // row stride of [row][dof] arrays: odd, so lanes walking rows hit distinct banks
-constexpr int kPackedA = kMaxRows * (kMaxRows + 1) / 2;   // A = J M^-1 J^T + R: lower triangle, row-packed
 TREE_HD int tri(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
 
 // ---------------------------------------------------------------------------------------------- tile runtime
@@ -42,13 +41,8 @@ struct Tile {
 #if defined(__CUDACC__)
   int lane;
   unsigned mask;
-  int cta_phase_sync;     // > 0: the tiles of a CTA also meet at the phase boundaries inside a step (k_tree_step sets it)
-  // CTA-wide rendezvous at a phase boundary of tree_step: every tile of the CTA walks the same phases, so that they
-  // stream through the same code together (instruction-cache sharing)
-  __device__ __forceinline__ void phase() const { if (cta_phase_sync) __syncthreads(); }
   __device__ __forceinline__ static Tile make() {
     Tile t;
-    t.cta_phase_sync = 0;
     const unsigned l = threadIdx.x & 31u;
     t.lane = (int)(l & (unsigned)(LANES - 1));
     t.mask = LANES == 32 ? 0xffffffffu : (((1u << (LANES & 31)) - 1u) << (l & ~(unsigned)(LANES - 1)));
@@ -64,14 +58,17 @@ struct Tile {
   int lane;
   static Tile make() { Tile t; t.lane = 0; return t; }
   void sync() const {}
-  void phase() const {}
   template <typename V> V sum(V v) const { return v; }
 #endif
 };
 
 // ---------------------------------------------------------------------------------------------- per-env scratch
-template <typename T>
+// ROWS / CON: constraint-row and contact capacity of this instantiation (njmax / nconmax).  The kernels run a small
+// capacity first (kFastRows rows: one register slot per lane, 11.5 KB per env) and hand the rare env that needs more to the
+// full-capacity instantiation (tree_kernels.cuh), so capacity never changes a result.
+template <typename T, int ROWS = kMaxRows, int CON = kMaxCon>
 struct Scratch {
+  static constexpr int kRows = ROWS, kCon = CON, kPackedA = ROWS * (ROWS + 1) / 2;
   // state (q: base position, quaternion w x y z, hinge angles)
   T q[kMaxDof + 1], qd[kMaxDof], warm[kMaxDof], ctrl[kMaxAct];
   // kinematics about the base position, world axes
@@ -81,9 +78,9 @@ struct Scratch {
   // of the constraint solve are born later: they share storage
   union {
     struct { T V[kMaxLinks][6], A[kMaxLinks][6], F[kMaxLinks][6]; };
-    struct { T r_pos[kMaxRows], r_R[kMaxRows], r_aref[kMaxRows], r_b[kMaxRows], r_f[kMaxRows]; };
+    struct { T r_pos[ROWS], r_R[ROWS], r_aref[ROWS], r_b[ROWS], r_f[ROWS]; };
   };
-  T r_acc[kMaxRows];
+  T r_acc[ROWS];
   T Ic[kMaxLinks][10];                 // mass, h = m c (3), inertia about the origin xx yy zz xy xz yz
   T gw[kMaxGeoms][6];                  // geom points in the world frame (relative to the base)
   // ONE square array for the mass matrix and its factor: strict upper triangle = M (symmetric), lower triangle incl. the
@@ -91,18 +88,19 @@ struct Scratch {
   T L[kMaxDof * kLD], Mdiag[kMaxDof], dinv[kMaxDof];
   T qfrc[kMaxDof], qacc_s[kMaxDof], qacc[kMaxDof], qfc[kMaxDof], tmp[kMaxDof], wk[kMaxDof];
   // contacts
-  int ncon, nefc, n_dropped, sweeps;
+  int ncon, nefc, n_dropped, sweeps, overflow;   // overflow: this step needed more rows / contacts than ROWS / CON
   unsigned char slot_on[2 * kMaxPairs];
-  int c_pair[kMaxCon], c_end[kMaxCon], c_dim[kMaxCon];
-  T c_dist[kMaxCon], c_pos[kMaxCon][3], c_frame[kMaxCon][9];
+  int c_pair[CON], c_end[CON], c_dim[CON];
+  T c_dist[CON], c_pos[CON][3], c_frame[CON][9];
   // constraint rows
-  signed char r_type[kMaxRows], r_sub[kMaxRows];
-  short r_id[kMaxRows];
-  T J[kMaxRows * kLD];                 // constraint Jacobian, overwritten by Y = L^-1 J^T (row r = y_r^T) before the solve
+  signed char r_type[ROWS], r_sub[ROWS];
+  short r_id[ROWS];
+  T J[ROWS * kLD];                 // constraint Jacobian, overwritten by Y = L^-1 J^T (row r = y_r^T) before the solve
   T Am[kPackedA];
+  static_assert(5 * ROWS <= 3 * kMaxLinks * 6, "the row vectors must fit in the storage of V, A, F");
+  static_assert(ROWS <= 64, "row kinds are kept in 64-bit masks");
 };
-static_assert(5 * kMaxRows <= 3 * kMaxLinks * 6, "the row vectors must fit in the storage of V, A, F");
-static_assert(kMaxRows <= 64, "row kinds are kept in 64-bit masks");
+constexpr int kFastRows = 32, kFastCon = 9;   // the common-case capacity (6 connect rows + 8 condim-3 contacts + 2 limits)
 
 enum RowType { kRowEq = 0, kRowLimit = 1, kRowContact = 2 };
 constexpr double kMinVal = 1e-15;
@@ -195,8 +193,8 @@ template <typename T> TREE_HD void jac_col(T* r, const T* S, const T* P) {
 
 // ---------------------------------------------------------------------------------------------- kinematics + dynamics
 // One link: frame, motion subspace, velocity, velocity-product acceleration, own spatial inertia and RNE force.
-template <typename T>
-TREE_FN void link_pass(const TreeModel<T>& m, Scratch<T>& s, int l) {
+template <typename T, typename SC>
+TREE_FN void link_pass(const TreeModel<T>& m, SC& s, int l) {
   T* pos = s.xpos[l];
   T* mat = s.xmat[l];
   T Vl[6], Al[6];
@@ -271,8 +269,8 @@ TREE_FN void link_pass(const TreeModel<T>& m, Scratch<T>& s, int l) {
 }
 
 // mj_kinematics + mj_comVel + mj_crb + mj_rne: frames, M (with armature), bias in s.tmp
-template <int LANES, typename T>
-TREE_FN void dynamics(const Tile<LANES>& tl, const TreeModel<T>& m, Scratch<T>& s) {
+template <int LANES, typename T, typename SC>
+TREE_FN void dynamics(const Tile<LANES>& tl, const TreeModel<T>& m, SC& s) {
   for (int lev = 0; lev < m.nlevels; lev++) {
     for (int i = m.level_off[lev] + tl.lane; i < m.level_off[lev + 1]; i += LANES) link_pass(m, s, i);
     tl.sync();
@@ -306,8 +304,8 @@ TREE_FN void dynamics(const Tile<LANES>& tl, const TreeModel<T>& m, Scratch<T>& 
 // dense Cholesky of (M + diag(add)) into s.L (lower triangle) and s.dinv = 1 / L_kk.  Left-looking, rows owned by fixed
 // lanes, ONE tile barrier per column: the running diagonal wk[i] = M_ii - sum_{j<k} L_ij^2 is kept by the owner of row i,
 // so the pivot of column k is one shared-memory read; L[i][k] = (M[i][k] - sum_j L[i][j] L[k][j]) / L[k][k].
-template <int LANES, typename T>
-TREE_FN void cholesky(const Tile<LANES>& tl, int n, Scratch<T>& s, const T* add, T scale) {
+template <int LANES, typename T, typename SC>
+TREE_FN void cholesky(const Tile<LANES>& tl, int n, SC& s, const T* add, T scale) {
   for (int i = tl.lane; i < n; i += LANES) s.wk[i] = s.Mdiag[i] + (add ? scale * add[i] : (T)0);
   tl.sync();
   for (int k = 0; k < n; k++) {
@@ -329,8 +327,8 @@ TREE_FN void cholesky(const Tile<LANES>& tl, int n, Scratch<T>& s, const T* add,
 
 // x <- L^-T x for one vector in shared memory, cooperative: the finished entries go to `out` (a different array), so a
 // column needs ONE barrier
-template <int LANES, typename T>
-TREE_FN void backward_one(const Tile<LANES>& tl, int n, const Scratch<T>& s, T* x, T* out) {
+template <int LANES, typename T, typename SC>
+TREE_FN void backward_one(const Tile<LANES>& tl, int n, const SC& s, T* x, T* out) {
   for (int k = n - 1; k >= 0; k--) {
     const T xk = x[k] * s.dinv[k];
     if (tl.lane == 0) out[k] = xk;
@@ -340,8 +338,8 @@ TREE_FN void backward_one(const Tile<LANES>& tl, int n, const Scratch<T>& s, T* 
 }
 
 // x <- (L L^T)^-1 x for one vector in shared memory, cooperative (column sweeps, one FMA per lane and step); s.wk is scratch
-template <int LANES, typename T>
-TREE_FN void solve_one(const Tile<LANES>& tl, int n, Scratch<T>& s, T* x) {
+template <int LANES, typename T, typename SC>
+TREE_FN void solve_one(const Tile<LANES>& tl, int n, SC& s, T* x) {
   for (int k = 0; k < n; k++) {
     const T xk = x[k] * s.dinv[k];
     if (tl.lane == 0) s.wk[k] = xk;
@@ -352,8 +350,8 @@ TREE_FN void solve_one(const Tile<LANES>& tl, int n, Scratch<T>& s, T* x) {
 }
 
 // one lane, one right-hand side: x <- L^-1 x (forward substitution, serial)
-template <typename T>
-TREE_FN void forward_row(int n, const Scratch<T>& s, T* x) {
+template <typename T, typename SC>
+TREE_FN void forward_row(int n, const SC& s, T* x) {
   for (int i = 0; i < n; i++) {
     T v = x[i];
     TREE_UNROLL4
@@ -364,8 +362,8 @@ TREE_FN void forward_row(int n, const Scratch<T>& s, T* x) {
 
 // ---------------------------------------------------------------------------------------------- collision
 // signed distance of the sphere of radius r at c to the world plane (base-relative coordinates)
-template <typename T>
-TREE_FN T plane_dist(const TreeModel<T>& m, const Scratch<T>& s, const T* c, T r) {
+template <typename T, typename SC>
+TREE_FN T plane_dist(const TreeModel<T>& m, const SC& s, const T* c, T r) {
   T d[3] = {c[0] - (m.plane_pos[0] - s.q[0]), c[1] - (m.plane_pos[1] - s.q[1]), c[2] - (m.plane_pos[2] - s.q[2])};
   return dot3(d, m.plane_n) - r;
 }
@@ -386,8 +384,8 @@ TREE_FN T seg_seg(const T* a0, const T* a1, const T* b0, const T* b1, T* pa, T* 
 }
 
 // mj_collision: geoms to the world frame, narrow phase per pair in MuJoCo's pair order, contacts compacted in that order
-template <int LANES, typename T>
-TREE_FN void collide(const Tile<LANES>& tl, const TreeModel<T>& m, Scratch<T>& s) {
+template <int LANES, typename T, typename SC>
+TREE_FN void collide(const Tile<LANES>& tl, const TreeModel<T>& m, SC& s) {
   for (int g = tl.lane; g < m.ng; g += LANES) {
     const int l = m.g_link[g];
     T t[3];
@@ -418,14 +416,14 @@ TREE_FN void collide(const Tile<LANES>& tl, const TreeModel<T>& m, Scratch<T>& s
   for (int sl = 0; sl < 2 * m.npair; sl++) {
     if (!s.slot_on[sl]) continue;
     const int dim = m.pair_condim[sl >> 1];
-    if (n < kMaxCon && rows + dim <= kMaxRows) {
+    if (n < SC::kCon && rows + dim <= SC::kRows) {
       if (tl.lane == 0) { s.c_pair[n] = sl >> 1; s.c_end[n] = sl & 1; s.c_dim[n] = dim; }
       n++;
       rows += dim;
     } else
       dropped++;
   }
-  if (tl.lane == 0) { s.ncon = n; s.n_dropped = dropped; }
+  if (tl.lane == 0) { s.ncon = n; s.n_dropped = dropped; s.overflow = dropped > 0; }
   tl.sync();
   for (int c = tl.lane; c < n; c += LANES) {
     const int p = s.c_pair[c], a = m.pair_a[p], b = m.pair_b[p];
@@ -464,8 +462,8 @@ TREE_FN void collide(const Tile<LANES>& tl, const TreeModel<T>& m, Scratch<T>& s
 
 // ---------------------------------------------------------------------------------------------- constraints
 // mj_makeConstraint + mj_makeImpedance: row table (connects, joint limits, contacts), Jacobians, R, aref
-template <int LANES, typename T>
-TREE_FN void make_rows(const Tile<LANES>& tl, const TreeModel<T>& m, Scratch<T>& s) {
+template <int LANES, typename T, typename SC>
+TREE_FN void make_rows(const Tile<LANES>& tl, const TreeModel<T>& m, SC& s) {
   if (tl.lane == 0) {
     int n = 0, crows = 0;
     for (int c = 0; c < s.ncon; c++) crows += s.c_dim[c];
@@ -476,8 +474,8 @@ TREE_FN void make_rows(const Tile<LANES>& tl, const TreeModel<T>& m, Scratch<T>&
       if (!m.limited[d]) continue;
       const T qv = s.q[d + 1];
       // lower side first (mj_instantiateLimit); the rows left after the contacts' reservation bound the count
-      if (qv - m.range[d][0] < 0 && n + crows < kMaxRows) { s.r_type[n] = kRowLimit; s.r_id[n] = d; s.r_sub[n] = 0; n++; }
-      if (m.range[d][1] - qv < 0 && n + crows < kMaxRows) { s.r_type[n] = kRowLimit; s.r_id[n] = d; s.r_sub[n] = 1; n++; }
+      if (qv - m.range[d][0] < 0) { if (n + crows < SC::kRows) { s.r_type[n] = kRowLimit; s.r_id[n] = d; s.r_sub[n] = 0; n++; } else s.overflow = 1; }
+      if (m.range[d][1] - qv < 0) { if (n + crows < SC::kRows) { s.r_type[n] = kRowLimit; s.r_id[n] = d; s.r_sub[n] = 1; n++; } else s.overflow = 1; }
     }
     for (int c = 0; c < s.ncon; c++)
       for (int k = 0; k < s.c_dim[c]; k++) { s.r_type[n] = kRowContact; s.r_id[n] = c; s.r_sub[n] = k; n++; }
@@ -584,8 +582,8 @@ TREE_FN int qcqp2(T* res, const T* Ain, const T* bin, const T* dd, T r) {
 }
 
 // mj_fwdConstraint: b, A = J M^-1 J^T + R, warm start, PGS (mj_solPGS), qacc, constraint force
-template <int LANES, typename T>
-TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scratch<T>& s) {
+template <int LANES, typename T, typename SC>
+TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, SC& s) {
   const int nv = m.nv, nefc = s.nefc;
   if (nefc == 0) {
     for (int d = tl.lane; d < nv; d += LANES) { s.qacc[d] = s.qacc_s[d]; s.qfc[d] = 0; }
@@ -672,7 +670,7 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
     // on registers -- no shared-memory traffic for acc / f and no barrier inside the sweep.  Same arithmetic as the general
     // path below (tests/test_gpu_tree.py runs the fp64 parity cases on 8, 16 and 32 lanes; the CPU harness runs the
     // general path).
-    constexpr int K = (kMaxRows + LANES - 1) / LANES;
+    constexpr int K = (SC::kRows + LANES - 1) / LANES;
     T acc[K], fr[K];
     int rb[K];
 #pragma unroll
@@ -893,8 +891,11 @@ TREE_FN void solve_constraints(const Tile<LANES>& tl, const TreeModel<T>& m, Scr
 struct TreeStats { int nefc, ncon, sweeps, dropped; };
 
 // one simulator step on the state held in the scratch block (s.q, s.qd, s.warm); u = the nu motor controls
-template <int LANES, typename T>
-TREE_FN void tree_step(const Tile<LANES>& tl, const TreeModel<T>& m, Scratch<T>& s, const T* u, TreeStats* st) {
+// abort_on_overflow: when the step needs more constraint rows / contacts than this instantiation holds, leave the state
+// UNTOUCHED and return false (the caller hands the env to the full-capacity instantiation); otherwise the surplus is
+// dropped in pair order and counted, like MuJoCo's njmax / nconmax
+template <int LANES, typename T, typename SC>
+TREE_FN bool tree_step(const Tile<LANES>& tl, const TreeModel<T>& m, SC& s, const T* u, TreeStats* st, bool abort_on_overflow = false) {
   const int nv = m.nv;
   dynamics(tl, m, s);                                      // frames, M, bias -> s.tmp
   // smooth force: passive damping - bias + actuation (ctrl clamped to ctrlrange, gear)
@@ -907,17 +908,14 @@ TREE_FN void tree_step(const Tile<LANES>& tl, const TreeModel<T>& m, Scratch<T>&
       s.qfrc[m.act_dof[a]] += m.act_gear[a] * c;
     }
   tl.sync();
-  tl.phase();
   cholesky(tl, nv, s, (const T*)nullptr, (T)0);
   for (int d = tl.lane; d < nv; d += LANES) s.qacc_s[d] = s.qfrc[d];
   tl.sync();
   solve_one(tl, nv, s, s.qacc_s);
-  tl.phase();
   collide(tl, m, s);
   make_rows(tl, m, s);
-  tl.phase();
+  if (abort_on_overflow && s.overflow) return false;       // tile-uniform (read after make_rows' barrier); q, qd, warm not yet written
   solve_constraints(tl, m, s);
-  tl.phase();
   // mj_Euler: (M + h D) qacc' = qfrc_smooth + qfrc_constraint; qvel += h qacc'; qpos integrated with the NEW velocity
   const T h = m.timestep;
   cholesky(tl, nv, s, m.damping, h);
@@ -949,6 +947,7 @@ TREE_FN void tree_step(const Tile<LANES>& tl, const TreeModel<T>& m, Scratch<T>&
   }
   tl.sync();
   if (st) { st->nefc = s.nefc; st->ncon = s.ncon; st->sweeps = s.sweeps; st->dropped += s.n_dropped; }
+  return true;
 }
 
 }  // namespace tree

@@ -24,6 +24,7 @@ struct TreeBatchView {
   int32_t* resets; // [n] auto-resets so far
   int32_t* order;  // [n] tile slot -> env: envs binned by the row count of their last step (k_tree_bin_*), or nullptr
   int32_t* bins;   // [2 * kTreeBins] histogram / cursors of that binning
+  int32_t* resume; // [n] substeps of the current launch an env has completed (two-pass scheme, k_tree_step)
 };
 constexpr int kTreeBins = 64;
 
@@ -37,16 +38,21 @@ struct TreeStepArgs {
   const void* reset_qd; // real [nv] device
 };
 
-template <typename T, int LANES>
+// MODE 0: single pass with this capacity (surplus rows / contacts are dropped and counted).
+// MODE 1: fast pass: an env whose step needs more than ROWS rows / CON contacts stops BEFORE that step (state untouched),
+//         is stored as it is and leaves the number of substeps it completed in v.resume[e].
+// MODE 2: continuation pass with the full capacity: only envs with resume[e] < n_sub run, from that substep on.
+// An env's result is therefore the full-capacity result whatever pass computed it (tests/test_gpu_tree.py).
+template <typename T, int LANES, int ROWS, int CON, int MODE>
 __global__ void __launch_bounds__(kTreeMaxBlock)
 k_tree_step(const __grid_constant__ TreeModel<T> m, const TreeBatchView<T> v, const T* __restrict__ action, int n_sub, T z_done,
             int auto_reset, uint8_t* __restrict__ done, const T* __restrict__ reset_q, const T* __restrict__ reset_qd,
             int step_barrier) {
   // the model (5.9 KB in fp32) is a __grid_constant__ kernel parameter: it lives in the constant bank, is read with
   // tile-uniform addresses, and costs no shared memory (shared memory is what bounds the resident envs per SM)
+  typedef Scratch<T, ROWS, CON> SC;
   extern __shared__ __align__(16) unsigned char tree_smem[];
-  Tile<LANES> tl = Tile<LANES>::make();
-  tl.cta_phase_sync = step_barrier < 0 ? 1 : 0;     // CASSIE3D_STEP_BARRIER=-1: also at the phase boundaries inside a step
+  const Tile<LANES> tl = Tile<LANES>::make();
   const int tile_in_block = (int)threadIdx.x / LANES, tiles_per_block = (int)blockDim.x / LANES;
   const int e_raw = (int)blockIdx.x * tiles_per_block + tile_in_block;
   const bool active = e_raw < v.n;           // surplus tiles shadow the last env (they take part in the CTA barriers) and store nothing
@@ -54,7 +60,12 @@ k_tree_step(const __grid_constant__ TreeModel<T> m, const TreeBatchView<T> v, co
   // the tiles of a CTA run in lock step, so a CTA is as slow as its env with the most constraint rows: slots are handed
   // out in the order of the last step's row counts (envs of similar cost share a CTA); results do not depend on it
   const int e = v.order ? v.order[slot] : slot;
-  Scratch<T>& s = *reinterpret_cast<Scratch<T>*>(tree_smem + (size_t)tile_in_block * sizeof(Scratch<T>));
+  int k0 = 0;
+  if (MODE == 2) {                           // no CTA barrier in this pass: tiles without work leave at once
+    k0 = v.resume[e];
+    if (!active || k0 >= n_sub) return;
+  }
+  SC& s = *reinterpret_cast<SC*>(tree_smem + (size_t)tile_in_block * sizeof(SC));
   const int nq = m.nq, nv = m.nv, nu = m.nu;
   const T* gq = v.qpos + (size_t)e * nq;
   const T* gv = v.qvel + (size_t)e * nv;
@@ -63,21 +74,23 @@ k_tree_step(const __grid_constant__ TreeModel<T> m, const TreeBatchView<T> v, co
   for (int d = 6 + tl.lane; d < nv; d += LANES) s.q[d + 1] = gq[m.user_dof[d] + 1];
   for (int d = tl.lane; d < nv; d += LANES) { s.qd[d] = gv[m.user_dof[d]]; s.warm[d] = gw[m.user_dof[d]]; }
   for (int a = tl.lane; a < nu; a += LANES) s.ctrl[a] = action ? action[(size_t)e * nu + a] : (T)0;
-  if (tl.lane == 0) s.n_dropped = 0;
+  if (tl.lane == 0) { s.n_dropped = 0; s.overflow = 0; }
   tl.sync();
   TreeStats st = {0, 0, 0, 0};
-  for (int k = 0; k < n_sub; k++) {
+  int k_done = n_sub;
+  bool alive = true;
+  for (int k = k0; k < n_sub; k++) {
     // lock step of the CTA's tiles: the once-per-step code is ~10 k straight-line instructions, and tiles that run through
     // it together share the instruction-cache fills (+15 %, profiles/r2v_sweep.txt; CASSIE3D_STEP_BARRIER=0 turns it off)
-    if (step_barrier < 0 || (step_barrier > 0 && k % step_barrier == 0)) __syncthreads();   // every step_barrier-th simulator step
-    tree_step(tl, m, s, s.ctrl, &st);
+    if (MODE != 2 && step_barrier > 0 && k % step_barrier == 0) __syncthreads();   // every step_barrier-th simulator step
+    if (alive && !tree_step(tl, m, s, s.ctrl, &st, MODE == 1)) { alive = false; k_done = k; }
   }
-  // termination (every lane evaluates it on the shared state) and auto-reset
+  // termination (every lane evaluates it on the shared state) and auto-reset -- not for an env that is handed on
   bool bad = false;
   for (int i = 0; i < nq; i++) bad = bad || !isfinite(s.q[i]);
   for (int i = 0; i < nv; i++) bad = bad || !isfinite(s.qd[i]);
   const bool fell = z_done > 0 && s.q[2] < z_done;
-  const bool is_done = bad || fell;
+  const bool is_done = alive && (bad || fell);
   tl.sync();
   if (is_done && auto_reset) {
     for (int i = tl.lane; i < 7; i += LANES) s.q[i] = reset_q[i];
@@ -93,12 +106,15 @@ k_tree_step(const __grid_constant__ TreeModel<T> m, const TreeBatchView<T> v, co
   for (int d = 6 + tl.lane; d < nv; d += LANES) oq[m.user_dof[d] + 1] = s.q[d + 1];
   for (int d = tl.lane; d < nv; d += LANES) { ov[m.user_dof[d]] = s.qd[d]; ow[m.user_dof[d]] = s.warm[d]; }
   if (tl.lane == 0) {
-    if (done) done[e] = bad ? 2 : (fell ? 1 : 0);
-    if (n_sub > 0) {
-      v.stats[4 * e + 0] = st.nefc; v.stats[4 * e + 1] = st.ncon; v.stats[4 * e + 2] = st.sweeps;
-      v.stats[4 * e + 3] += st.dropped;
+    if (MODE != 0) v.resume[e] = k_done;
+    if (alive) {
+      if (done) done[e] = bad ? 2 : (fell ? 1 : 0);
+      if (n_sub > k0) {
+        v.stats[4 * e + 0] = st.nefc; v.stats[4 * e + 1] = st.ncon; v.stats[4 * e + 2] = st.sweeps;
+        v.stats[4 * e + 3] += st.dropped;
+      }
+      if (is_done && auto_reset) v.resets[e] += 1;
     }
-    if (is_done && auto_reset) v.resets[e] += 1;
   }
 }
 
@@ -138,45 +154,65 @@ struct TreeLaunch {
   static cudaError_t set_all(const TreeBatchView<T>& v, int nq, int nv, const T* q, const T* qd, const uint8_t* mask, cudaStream_t s);
 };
 
+// tiles (envs) per CTA of one kernel instantiation: shared memory is the resource (one Scratch block per env).  Two
+// resident CTAs per SM with as many tiles each as fit; the tiles of a CTA run in lock step and share their
+// instruction-cache fills (profiles/r2aa_tree_sweep_v7.txt).  CASSIE3D_TILES overrides.  Whole warps only.
+template <typename K>
+inline int tree_tiles(K kernel, size_t scratch_bytes, int lanes, int want) {
+  int dev = 0, smem_sm = 0, smem_blk = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+  cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const int per_warp = 32 / lanes;
+  int t = want > 0 ? want : (smem_sm / 2 - 1024) / (int)scratch_bytes;
+  const int cap_blk = smem_blk / (int)scratch_bytes, cap_thr = kTreeMaxBlock / lanes;
+  if (t > cap_blk) t = cap_blk;
+  if (t > cap_thr) t = cap_thr;
+  t = t / per_warp * per_warp;
+  if (t < per_warp) t = per_warp;
+  if ((size_t)t * scratch_bytes > (size_t)smem_blk) return -1;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)t * scratch_bytes));
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  return t;
+}
+
 template <typename T, int LANES>
 inline cudaError_t launch_tree_step(const TreeModel<T>& m, const TreeBatchView<T>& v, const TreeStepArgs& a, cudaStream_t s) {
-  // Envs (tiles) per CTA: shared memory is the resource (one Scratch block per env).  Default: two resident CTAs per SM
-  // with as many tiles each as fit (7 in fp32): the tiles of a CTA run in lock step (k_tree_step) and share their
-  // instruction-cache fills (profiles/r2aa_tree_sweep_v7.txt: 9.3e6 vs 8.3e6 with two tiles); CASSIE3D_TILES overrides.
-  static int tiles = 0;
-  if (tiles == 0) {
-    int dev = 0, smem_sm = 0, smem_blk = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-    cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    const int per_warp = 32 / LANES;
-    int t = (smem_sm / 2 - 1024) / (int)sizeof(Scratch<T>);       // two resident CTAs per SM, as many tiles each as fit
-    if (const char* e = getenv("CASSIE3D_TILES")) t = atoi(e);
-    const int cap_blk = smem_blk / (int)sizeof(Scratch<T>), cap_thr = kTreeMaxBlock / LANES;
-    if (t > cap_blk) t = cap_blk;
-    if (t > cap_thr) t = cap_thr;
-    t = t / per_warp * per_warp;
-    if (t < per_warp) t = per_warp;
-    if ((size_t)t * sizeof(Scratch<T>) > (size_t)smem_blk) return cudaErrorInvalidConfiguration;
-    cudaFuncSetAttribute(k_tree_step<T, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)t * sizeof(Scratch<T>)));
-    cudaFuncSetAttribute(k_tree_step<T, LANES>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    tiles = t;
-  }
-  const int block = tiles * LANES;
-  const size_t dyn = (size_t)tiles * sizeof(Scratch<T>);
-  const unsigned grid = (unsigned)((v.n + tiles - 1) / tiles);
+  typedef Scratch<T, kFastRows, kFastCon> Fast;
+  typedef Scratch<T, kMaxRows, kMaxCon> Full;
+  static const int env_tiles = [] { const char* e = getenv("CASSIE3D_TILES"); return e ? atoi(e) : 0; }();
   static const int step_barrier = [] { const char* e = getenv("CASSIE3D_STEP_BARRIER"); return e ? atoi(e) : 1; }();
   static const int sort_envs = [] { const char* e = getenv("CASSIE3D_SORT"); return e ? atoi(e) : 0; }();   // measured +1 %: off by default (profiles/r2ac_tree_lockstep.txt)
+  // CASSIE3D_TWO_PASS=0: one pass with the full capacity (the round-2 v8 kernel); default: fast capacity first, the rare
+  // env that needs more rows continues in a full-capacity pass (profiles/r2al_two_pass.txt)
+  static const int two_pass = [] { const char* e = getenv("CASSIE3D_TWO_PASS"); return e ? atoi(e) : 1; }();
+  static const int t_single = tree_tiles(k_tree_step<T, LANES, kMaxRows, kMaxCon, 0>, sizeof(Full), LANES, env_tiles);
+  static const int t_fast = tree_tiles(k_tree_step<T, LANES, kFastRows, kFastCon, 1>, sizeof(Fast), LANES, env_tiles);
+  static const int t_cont = tree_tiles(k_tree_step<T, LANES, kMaxRows, kMaxCon, 2>, sizeof(Full), LANES, 32 / LANES);   // one warp per CTA: idle tiles leave at once
+  if (t_single < 0 || t_fast < 0 || t_cont < 0) return cudaErrorInvalidConfiguration;
   TreeBatchView<T> vv = v;
-  if (sort_envs && step_barrier && v.order && v.bins && tiles > 1) {
+  const int tiles0 = two_pass ? t_fast : t_single;
+  if (sort_envs && step_barrier && v.order && v.bins && tiles0 > 1) {
     k_tree_bin_hist<<<(v.n + 255) / 256, 256, 0, s>>>(v.n, v.stats, v.bins);
     k_tree_bin_scan<<<1, 1, 0, s>>>(v.bins);
     k_tree_bin_scatter<<<(v.n + 255) / 256, 256, 0, s>>>(v.n, v.stats, v.bins, v.order);
     count_launch(); count_launch(); count_launch();
   } else
     vv.order = nullptr;
-  k_tree_step<T, LANES><<<grid, block, dyn, s>>>(m, vv, (const T*)a.action, a.n_sub, (T)a.z_done, a.auto_reset, a.done,
-                                                   (const T*)a.reset_q, (const T*)a.reset_qd, step_barrier);
+  const T* act = (const T*)a.action;
+  const T *rq = (const T*)a.reset_q, *rv = (const T*)a.reset_qd;
+  if (!two_pass) {
+    k_tree_step<T, LANES, kMaxRows, kMaxCon, 0><<<(unsigned)((v.n + t_single - 1) / t_single), t_single * LANES, (size_t)t_single * sizeof(Full), s>>>(
+        m, vv, act, a.n_sub, (T)a.z_done, a.auto_reset, a.done, rq, rv, step_barrier);
+    count_launch();
+    return cudaGetLastError();
+  }
+  k_tree_step<T, LANES, kFastRows, kFastCon, 1><<<(unsigned)((v.n + t_fast - 1) / t_fast), t_fast * LANES, (size_t)t_fast * sizeof(Fast), s>>>(
+      m, vv, act, a.n_sub, (T)a.z_done, a.auto_reset, a.done, rq, rv, step_barrier);
+  count_launch();
+  vv.order = nullptr;
+  k_tree_step<T, LANES, kMaxRows, kMaxCon, 2><<<(unsigned)((v.n + t_cont - 1) / t_cont), t_cont * LANES, (size_t)t_cont * sizeof(Full), s>>>(
+      m, vv, act, a.n_sub, (T)a.z_done, a.auto_reset, a.done, rq, rv, 0);
   count_launch();
   return cudaGetLastError();
 }

@@ -147,6 +147,12 @@ class TreeHarness:
         fn(int(n), self.p(q), self.p(qd), self.p(warm), self.p(np.ascontiguousarray(u, np.float64)), self.ip(st))
         return st
 
+    def step_fast(self, q, qd, warm, u):
+        """the kernels' first pass: fast capacity, abort on overflow.  Returns (taken, stats)"""
+        st = np.zeros(4, np.int32)
+        ok = self.L.th_step_fast_f64(self.p(q), self.p(qd), self.p(warm), self.p(np.ascontiguousarray(u, np.float64)), self.ip(st))
+        return bool(ok), st
+
     def count_ops(self, q, qd, warm, u):
         out = np.zeros(6, np.int64)
         self.L.th_count_ops(self.p(np.ascontiguousarray(q, np.float64)), self.p(np.ascontiguousarray(qd, np.float64)),
@@ -174,6 +180,17 @@ def tree_harness(oracle):
 
 LEG_POSE_3D = [0.0, 0.0, 0.68111815, -1.40730357, 1.62972042, -1.77611107, -0.61968407]
 TORQUE_HIGH_3D = np.array([4.5, 4.5, 12.2, 12.2, 0.9] * 2)
+
+
+def lying3d(z=0.10, axis="x", angle=1.5708, straight=False):
+    """a robot pressed into the floor on its side / back: 9-10 contacts, 33-36 constraint rows (more than the fast capacity)"""
+    q = pose3d(z)
+    if straight:
+        q[7:14] = [0, 0, 0.0, -0.7, 1.0, -1.5, 0]; q[14:21] = q[7:14]
+    v = [np.cos(angle / 2), 0.0, 0.0, 0.0]
+    v[{"x": 1, "y": 2}[axis]] = np.sin(angle / 2)
+    q[3:7] = v
+    return q
 
 
 def pose3d(z=0.945):

@@ -156,6 +156,24 @@ void th_count_ops(const double* q, const double* qd, const double* warm, const d
   for (int i = 0; i < 4; i++) out[i] = g_ops[i];
   out[4] = st.nefc; out[5] = st.sweeps;
 }
+// one step with the FAST capacity and abort_on_overflow (the kernels' first pass): returns 1 when the step was taken, 0 when
+// it needs more rows / contacts (the state must then be untouched); stats as th_steps
+int th_step_fast_f64(double* q, double* qd, double* warm, const double* u, int* stats) {
+  const TreeModel<double>& m = g_m64;
+  static Scratch<double, kFastRows, kFastCon> s;
+  const Tile<1> tl = Tile<1>::make();
+  for (int i = 0; i < 7; i++) s.q[i] = q[i];
+  for (int d = 6; d < m.nv; d++) s.q[d + 1] = q[m.user_dof[d] + 1];
+  for (int d = 0; d < m.nv; d++) { s.qd[d] = qd[m.user_dof[d]]; s.warm[d] = warm[m.user_dof[d]]; }
+  TreeStats st = {0, 0, 0, 0};
+  s.n_dropped = 0; s.overflow = 0;
+  const bool ok = tree_step(tl, m, s, u, &st, true);
+  for (int i = 0; i < 7; i++) q[i] = s.q[i];
+  for (int d = 6; d < m.nv; d++) q[m.user_dof[d] + 1] = s.q[d + 1];
+  for (int d = 0; d < m.nv; d++) { qd[m.user_dof[d]] = s.qd[d]; warm[m.user_dof[d]] = s.warm[d]; }
+  if (stats) { stats[0] = s.nefc; stats[1] = s.ncon; stats[2] = st.sweeps; stats[3] = s.n_dropped; }
+  return ok ? 1 : 0;
+}
 void th_steps_f64(int n, double* q, double* qd, double* warm, const double* u, int* stats) { steps<double>(n, q, qd, warm, u, stats); }
 void th_steps_f32(int n, double* q, double* qd, double* warm, const double* u, int* stats) { steps<float>(n, q, qd, warm, u, stats); }
 }

@@ -4,7 +4,7 @@ step kernel (8, 16, 32 lanes per env) is checked.  Error metric as in tests/test
 import numpy as np
 import pytest
 
-from conftest import TORQUE_HIGH_3D, pose3d
+from conftest import TORQUE_HIGH_3D, lying3d, pose3d
 
 pytestmark = pytest.mark.gpu
 
@@ -210,3 +210,32 @@ def test_tree_big_ragged_batch_subset_vs_oracle(oracle, omodel3d):
     # an indexing mistake would be O(1); the fp32 level of a cold first step on penetrating toes is a few 1e-5 at worst
     # (the same envs give the same errors on the CPU harness), 1e-6 typically
     assert np.median(errs) < 1e-5 and errs.max() < 1e-4, errs
+
+
+@pytest.mark.parametrize("lanes", [8, 32])
+def test_tree_two_pass_overflow_vs_oracle(oracle, omodel3d, lanes):
+    """envs that need more than the fast capacity (32 rows / 9 contacts) mid-launch are finished by the full-capacity pass:
+    robots pressed into the floor (33 and 36 rows at the first step) between standing ones, fp64, 30 free-running steps in
+    three launches against the oracle (which has room for everything): 1e-8, nothing dropped"""
+    import torch
+    from cassierl_b200.envs3d import Cassie3dBatch
+    n, steps, hold = 13, 30, 10
+    q0, v0 = _starts(n, seed=21)
+    for e, q in ((2, lying3d(0.10, "x", 1.5708)), (3, lying3d(0.14, "y", -1.5708, straight=True)), (7, lying3d(0.12, "x", 1.5708, straight=True)),
+                 (12, lying3d(0.06, "y", 1.5708))):
+        q0[e] = q; v0[e] = 0
+    rng = np.random.default_rng(22)
+    A = rng.uniform(-1, 1, (n, steps // hold, 10)) * TORQUE_HIGH_3D
+    b = Cassie3dBatch(n, precision=64, lanes=lanes)
+    b.set_state(q0, v0)
+    rows_first = None
+    for k in range(steps // hold):
+        b.step(torch.tensor(A[:, k]), n=hold)
+    q, v = (x.cpu().numpy() for x in b.state())
+    st = b.stats().cpu().numpy()
+    b.close()
+    d = oracle.Data(omodel3d); d.set_state(q0[3], v0[3]); d.forward()
+    assert d.efc()["J"].shape[0] > 32                      # the scenario does exceed the fast capacity
+    _, qo, vo, _ = oracle.rollout_tree(omodel3d, q0, v0, steps, actions=A, hold=hold)
+    assert st[:, 3].sum() == 0
+    assert _err(q, v, qo, vo).max() < 1e-8, _err(q, v, qo, vo)

@@ -13,7 +13,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import ROOT, TORQUE_HIGH_3D, pose3d
+from conftest import ROOT, TORQUE_HIGH_3D, lying3d, pose3d
 
 
 def _err(q, v, qo, vo):
@@ -165,6 +165,29 @@ def test_tree_fp32_single_step(oracle, omodel3d, tree_harness):
     assert same.max() < 5e-5, same.max()                                  # the rest: a contact at its first touch
     assert mism.sum() <= 8, mism.sum()
     assert e.max() < 2e-2
+
+
+def test_tree_fast_capacity_aborts_cleanly(oracle, omodel3d, tree_harness):
+    """the kernels' first pass (32 rows / 9 contacts): a step that fits is the full-capacity step bit for bit; a step that
+    does not fit is refused with the state untouched, and the full capacity then takes it without dropping anything"""
+    th = tree_harness
+    # fits: standing robot after landing
+    q, v, w = pose3d(), np.zeros(20), np.zeros(20)
+    th.step(q, v, w, np.zeros(10), n=80)
+    qa, va, wa = q.copy(), v.copy(), w.copy()
+    ok, st = th.step_fast(qa, va, wa, np.zeros(10))
+    th.step(q, v, w, np.zeros(10))
+    assert ok and st[0] >= 12 and np.array_equal(qa, q) and np.array_equal(va, v) and np.array_equal(wa, w)
+    # does not fit: pressed into the floor on its side (33 rows) / on its back (36 rows, 10 contacts)
+    for q0 in (lying3d(0.10, "x", 1.5708), lying3d(0.14, "y", -1.5708, straight=True)):
+        q, v, w = q0.copy(), np.zeros(20), np.zeros(20)
+        ok, st = th.step_fast(q, v, w, np.zeros(10))
+        assert not ok and np.array_equal(q, q0) and not v.any() and not w.any()
+        full = th.step(q, v, w, np.zeros(10))
+        d = oracle.Data(omodel3d); d.set_state(q0, np.zeros(20)); d.step(np.zeros(10))
+        qo, vo = d.state()
+        assert full[0] == d.efc()["J"].shape[0] > 32 and full[3] == 0
+        assert _err(q, v, qo, vo) < 1e-9
 
 
 def test_tree_op_count(oracle, omodel3d, tree_harness):
