@@ -26,7 +26,9 @@ const char* Cassie3dGetLastError(void);
 /* xml_path NULL: the packaged physics-only rendition of cassie3d_stiff.xml (cassierl_b200/model/). */
 Cassie3dBatch* Cassie3dBatchCreate(const char* xml_path, int n_envs, int device, int precision);
 void Cassie3dBatchDestroy(Cassie3dBatch* h);
-/* out[0..5] = nq, nv, nu, constraint-row capacity, contact capacity, bytes of shared memory per env */
+/* out[0..5] = nq, nv, nu, constraint-row capacity, contact capacity (per env and step; what exceeds them is dropped in
+ * MuJoCo's pair order and counted in the stats), bytes of shared memory per env of the first pass (the step runs a small
+ * capacity first and finishes the rare env that needs more in a full-capacity continuation launch: same results) */
 int Cassie3dBatchSizes(Cassie3dBatch* h, int32_t* out);
 /* lanes per env of the step kernel: 8, 16 or 32 (default: env CASSIE3D_LANES, else 32) */
 int Cassie3dBatchSetLanes(Cassie3dBatch* h, int lanes);
