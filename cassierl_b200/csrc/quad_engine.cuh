@@ -16,6 +16,7 @@
 
 #ifdef CASSIE_HOST_HARNESS
 extern bool cassie_force_tier1;   // test hook: run the 16-row tier on states the 12-row tier could handle
+extern bool cassie_force_tier2;   // test hook: run the 20-row tier on states the smaller tiers could handle
 #endif
 
 namespace cassie {
@@ -395,19 +396,31 @@ QUAD_FN R dot8(const R J[8], const V8<R>& x) {
 //   tier 0 (common regime: standing, squatting, walking): 2 connect slots + 2 toe-contact slots per leg, 12 rows
 //   tier 1: + 2 joint-limit slots per leg, contact slots take any floor contact of the leg (leg 0 also the pelvis
 //           sphere), 16 rows
-//   anything else (3+ limits or 3+ contacts on one leg: robots lying on the floor) -> serial fallback.
+//   tier 2: + 4 joint-limit slots per leg (every limited joint of a leg at its stop: hip, knee, tarsus, toe -- robots
+//           in flight with the legs stretched, which is where random OSC accelerations send them), 20 rows.  Lane
+//           (L, h) owns the limits number h and 2 + h of leg L; the columns keep mj_makeConstraint's dof order
+//           (all of leg 0, then all of leg 1).
+//   anything else (3+ contacts on one leg: robots lying on the floor) -> serial fallback.
+constexpr int kRowSlots = 10;                      // row slots per leg reserved in PhysLayout::rowJ (tier 2 uses all)
 template <int TIER>
 struct Tier {
-  static constexpr int NSL = TIER ? 2 : 1;        // scalar rows per lane
+  static constexpr int NSL = TIER + 1;            // scalar rows per lane
   static constexpr int NS = 4 * NSL;              // scalar rows
   static constexpr int NR = NS + 8;               // rows
   static constexpr int LR = NR / 2;               // row slots per leg
   static constexpr int KO = NSL + 2;              // rows owned by a lane
   // leg-local slot of owned row k of half hh: k < NSL scalar kind k, then normal, tangent of contact hh
   static QUAD_FN int slot(int k, int hh) { return k < NSL ? 2 * k + hh : 2 * NSL + 2 * hh + (k - NSL); }
+  // global column (= PGS order) of the scalar row of kind k (0 connect, 1.. limit) owned by lane c = 2 Lc + hh
+  static QUAD_FN constexpr int scol(int k, int c) {
+    return (TIER < 2 || k == 0) ? 4 * k + c : 4 + 4 * (c >> 1) + 2 * (k - 1) + (c & 1);
+  }
+  // ... and back: kind and owner lane of scalar column i
+  static QUAD_FN constexpr int skind(int i) { return (TIER < 2 || i < 4) ? i >> 2 : 1 + (((i - 4) & 3) >> 1); }
+  static QUAD_FN constexpr int sown(int i) { return (TIER < 2 || i < 4) ? i & 3 : 2 * ((i - 4) >> 2) + ((i - 4) & 1); }
   // global column (= PGS order) of leg-local slot t of leg Lc
   static QUAD_FN constexpr int col(int Lc, int t) {
-    return t < 2 * NSL ? 4 * (t >> 1) + 2 * Lc + (t & 1) : NS + 2 * (2 * Lc + ((t - 2 * NSL) >> 1)) + ((t - 2 * NSL) & 1);
+    return t < 2 * NSL ? scol(t >> 1, 2 * Lc + (t & 1)) : NS + 2 * (2 * Lc + ((t - 2 * NSL) >> 1)) + ((t - 2 * NSL) & 1);
   }
 };
 
@@ -421,8 +434,8 @@ struct StateLayout {
 struct PhysLayout {
   static constexpr int ld1 = 0;                         // factor of M
   static constexpr int ld2 = ld1 + kLdSize;             // factor of M + h D (mj_Euler [EXT] implicit damping)
-  static constexpr int rowJ = ld2 + kLdSize;            // [leg][slot][8], 8 slots per leg reserved
-  static constexpr int end = rowJ + 2 * 8 * 8;
+  static constexpr int rowJ = ld2 + kLdSize;            // [leg][slot][8], kRowSlots slots per leg reserved
+  static constexpr int end = rowJ + 2 * kRowSlots * 8;
 };
 
 struct QStepStats {
@@ -477,7 +490,7 @@ QUAD_FN int quad_pgs(const PlanarModel<T>& m, const Lane ln, const T (&A)[Tier<T
   for (int k = 0; k < NSL; k++) {
     Ass[k] = T(1);
     CASSIE_UNROLL
-    for (int c = 0; c < 4; c++) Ass[k] = c == l ? A[k][4 * k + c] : Ass[k];
+    for (int c = 0; c < 4; c++) Ass[k] = c == l ? A[k][Q::scol(k, c)] : Ass[k];
   }
   CASSIE_UNROLL
   for (int p = 0; p < 4; p++) {
@@ -511,7 +524,7 @@ QUAD_FN int quad_pgs(const PlanarModel<T>& m, const Lane ln, const T (&A)[Tier<T
   CASSIE_UNROLL
   for (int k = 0; k < NSL; k++) {
     CASSIE_UNROLL
-    for (int c = 0; c < 4; c++) fall[4 * k + c] = shfl(f[k], c);
+    for (int c = 0; c < 4; c++) fall[Q::scol(k, c)] = shfl(f[k], c);
   }
   CASSIE_UNROLL
   for (int p = 0; p < 4; p++) { fall[NS + 2 * p] = shfl(f[NSL], p); fall[NS + 2 * p + 1] = shfl(f[NSL + 1], p); }
@@ -543,7 +556,7 @@ QUAD_FN int quad_pgs(const PlanarModel<T>& m, const Lane ln, const T (&A)[Tier<T
   T acc[KO];
   CASSIE_UNROLL
   for (int k = 0; k < KO; k++) {
-    const int row = k < NSL ? 4 * k + l : NS + 2 * l + (k - NSL);
+    const int row = k < NSL ? Q::scol(k, l) : NS + 2 * l + (k - NSL);
     T a = b[k];
     CASSIE_UNROLL
     for (int c = 0; c < NR; c++) a += (c >= row) ? A[k][c] * fall[c] : T(0);
@@ -571,11 +584,11 @@ QUAD_FN int quad_pgs(const PlanarModel<T>& m, const Lane ln, const T (&A)[Tier<T
     for (int k = 0; k < KO; k++) { so[k] = f[k]; cres[k] = T(0); }
     CASSIE_UNROLL
     for (int i = 0; i < NS; i++) {   // scalar rows: connects unbounded, joint limits f >= 0
-      const int ks = i >> 2;
-      const bool own = (i & 3) == l;
+      const int ks = Q::skind(i);
+      const bool own = Q::sown(i) == l;
       T fn_own = f[ks] - acc[ks] * inv[ks];
       if (ks >= 1) fn_own = Num<T>::max_(fn_own, T(0));
-      const T fn = shfl(fn_own, i & 3);
+      const T fn = shfl(fn_own, Q::sown(i));
       cres[ks] = own ? acc[ks] : cres[ks];
       f[ks] = own ? fn : f[ks];
       CASSIE_UNROLL
@@ -702,16 +715,19 @@ QUAD_FN void quad_constraints(const PlanarModel<T>& m, const Lane ln, SV<T> S, c
         for (int side = 0; side < 2; side++) {
           const T dist = side ? dhi : dlo;
           if (dist < T(0)) {
-            if (nlim == h) {
-              CASSIE_UNROLL
-              for (int c = 0; c < 8; c++) Jown[NSL - 1][c] = T(0);
-              const T sg = side ? T(-1) : T(1);
-              CASSIE_UNROLL
-              for (int c = 0; c < kLegLinks; c++) Jown[NSL - 1][3 + c] = c == a ? sg : T(0);
-              const T imp = impedance(m.lim_solimp, dist);
-              const T Rv = (T(1) - imp) * m.lim_diag[j] * Num<T>::rcp_(imp);
-              Rown[NSL - 1] = Rv > T(kMinVal) ? Rv : T(kMinVal);
-              b0[NSL - 1] = -(-Bd * (sg * qd.l[a]) - K * imp * dist);
+            CASSIE_UNROLL
+            for (int kl = 1; kl < NSL; kl++) {
+              if (nlim == 2 * (kl - 1) + h) {
+                CASSIE_UNROLL
+                for (int c = 0; c < 8; c++) Jown[kl][c] = T(0);
+                const T sg = side ? T(-1) : T(1);
+                CASSIE_UNROLL
+                for (int c = 0; c < kLegLinks; c++) Jown[kl][3 + c] = c == a ? sg : T(0);
+                const T imp = impedance(m.lim_solimp, dist);
+                const T Rv = (T(1) - imp) * m.lim_diag[j] * Num<T>::rcp_(imp);
+                Rown[kl] = Rv > T(kMinVal) ? Rv : T(kMinVal);
+                b0[kl] = -(-Bd * (sg * qd.l[a]) - K * imp * dist);
+              }
             }
             nlim++;
           }
@@ -772,7 +788,7 @@ QUAD_FN void quad_constraints(const PlanarModel<T>& m, const Lane ln, SV<T> S, c
   // ---- publish the Jacobians of the owned slots
   CASSIE_UNROLL
   for (int kk = 0; kk < KO; kk++) {
-    const SV<T> dst = S.at(P::rowJ + (L * 8 + Q::slot(kk, h)) * 8);
+    const SV<T> dst = S.at(P::rowJ + (L * kRowSlots + Q::slot(kk, h)) * 8);
     CASSIE_UNROLL
     for (int c = 0; c < 8; c++) dst[c] = Jown[kk][c];
   }
@@ -794,7 +810,7 @@ QUAD_FN void quad_constraints(const PlanarModel<T>& m, const Lane ln, SV<T> S, c
     V8<T> x[NB];
     CASSIE_UNROLL
     for (int r = 0; r < NB; r++) {
-      const SV<T> src = S.at(P::rowJ + (h * 8 + t0 + r) * 8);
+      const SV<T> src = S.at(P::rowJ + (h * kRowSlots + t0 + r) * 8);
       CASSIE_UNROLL
       for (int bb = 0; bb < 3; bb++) x[r].b[bb] = src[bb];
       CASSIE_UNROLL
@@ -806,7 +822,7 @@ QUAD_FN void quad_constraints(const PlanarModel<T>& m, const Lane ln, SV<T> S, c
       // the partner's row of the same kind, from shared memory
       const int sp = Q::slot(kk, 1 - h), so = Q::slot(kk, h);
       T Jp[8];
-      const SV<T> src = S.at(P::rowJ + (L * 8 + sp) * 8);
+      const SV<T> src = S.at(P::rowJ + (L * kRowSlots + sp) * 8);
       CASSIE_UNROLL
       for (int c = 0; c < 8; c++) Jp[c] = src[c];
       CASSIE_UNROLL
@@ -841,7 +857,7 @@ QUAD_FN void quad_constraints(const PlanarModel<T>& m, const Lane ln, SV<T> S, c
     CASSIE_UNROLL
     for (int kk = 0; kk < KO; kk++) {
       const T fo = fown[kk], fp = shx(fown[kk], 1);
-      const SV<T> src = S.at(P::rowJ + (L * 8 + Q::slot(kk, 1 - h)) * 8);
+      const SV<T> src = S.at(P::rowJ + (L * kRowSlots + Q::slot(kk, 1 - h)) * 8);
       CASSIE_UNROLL
       for (int bb = 0; bb < 3; bb++) pb[bb] += Jown[kk][bb] * fo + src[bb] * fp;
       CASSIE_UNROLL
@@ -919,10 +935,12 @@ QUAD_FN void quad_physics_step(const PlanarModel<T>& m, const PlanarModel<TG>& m
   if (L == 0) ncon_other += sph_dist <= T(0);
   ncon = ncon_other + (cdist[kToe][0] <= T(0)) + (cdist[kToe][1] <= T(0));
   bool tier1 = nlim > 0 || ncon_other > 0;
-  bool general = nlim > 2 || ncon > 2;
+  bool tier2 = nlim > 2;
+  bool general = nlim > 4 || ncon > 2;
 #ifdef CASSIE_HOST_HARNESS
   general = general || cassie_force_general_path;
   tier1 = tier1 || cassie_force_tier1;
+  tier2 = tier2 || cassie_force_tier2;
 #endif
   // The tier is chosen per WARP (the shuffles of a tier name all 32 lanes).  The two tiers agree bit for bit on the envs
   // both can handle (inert rows contribute exact zeros), and an env outside both ("general": robots lying on the floor)
@@ -930,6 +948,7 @@ QUAD_FN void quad_physics_step(const PlanarModel<T>& m, const PlanarModel<TG>& m
   // the thread-per-env engine -- so an env's result never depends on its warp mates.
   general = qany(general);
   const bool any_general = wany(general);
+  const bool use_t2 = wany(tier2);
   const bool use_t1 = wany(tier1 || general);
   leg_fk_velocities(m, L, qd, k);
 
@@ -975,7 +994,8 @@ QUAD_FN void quad_physics_step(const PlanarModel<T>& m, const PlanarModel<TG>& m
   V8<T> fc;
   int sweeps, nrows;
   unsigned mask;
-  if (use_t1) quad_constraints<1>(m, ln, S, k, q, qd, qs, warm, eq_rx, eq_rz, cdist, sph_dist, fc, &sweeps, &nrows, &mask);
+  if (use_t2) quad_constraints<2>(m, ln, S, k, q, qd, qs, warm, eq_rx, eq_rz, cdist, sph_dist, fc, &sweeps, &nrows, &mask);
+  else if (use_t1) quad_constraints<1>(m, ln, S, k, q, qd, qs, warm, eq_rx, eq_rz, cdist, sph_dist, fc, &sweeps, &nrows, &mask);
   else quad_constraints<0>(m, ln, S, k, q, qd, qs, warm, eq_rx, eq_rz, cdist, sph_dist, fc, &sweeps, &nrows, &mask);
 
   // ---- qacc = qacc_smooth + M^-1 qfrc_constraint, mj_Euler [EXT]: (M + h D) qacc' = qfrc_smooth + qfrc_constraint

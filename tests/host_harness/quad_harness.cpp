@@ -13,6 +13,7 @@
 using namespace cassie;
 bool cassie_force_general_path = false;
 bool cassie_force_tier1 = false;
+bool cassie_force_tier2 = false;
 
 static FlatModels g_models;
 static std::string g_err;
@@ -90,6 +91,7 @@ int qh_load(const char* path) { return flatten_mjcf_file(path, &g_models, &g_err
 const char* qh_error() { return g_err.c_str(); }
 void qh_force_general_path(int on) { cassie_force_general_path = on != 0; }
 void qh_force_tier1(int on) { cassie_force_tier1 = on != 0; }
+void qh_force_tier2(int on) { cassie_force_tier2 = on != 0; }
 void qh_steps_f64(int n, double* q, double* qd, double* warm, const double* u, int* nrows, int* sweeps, unsigned* mask) {
   run_steps<double>(n, q, qd, warm, u, nrows, sweeps, mask);
 }
