@@ -792,7 +792,7 @@ QUAD_FN void quad_constraints(const PlanarModel<T>& m, const Lane ln, SV<T> S, c
     CASSIE_UNROLL
     for (int c = 0; c < 8; c++) dst[c] = Jown[kk][c];
   }
-  const bool narrow = !wany(ncon > 1);
+  const bool narrow = !cta_any(ncon > 1);
   wsync();
 
   // ---- b = J qacc_smooth - aref, jar = J qacc_warmstart - aref of the owned rows
@@ -948,8 +948,10 @@ QUAD_FN void quad_physics_step(const PlanarModel<T>& m, const PlanarModel<TG>& m
   // the thread-per-env engine -- so an env's result never depends on its warp mates.
   general = qany(general);
   const bool any_general = wany(general);
-  const bool use_t2 = wany(tier2);
-  const bool use_t1 = wany(tier1 || general);
+  // ... and per CTA where several warps run in lock step: seven warps in three different tiers would each pull their own
+  // unrolled code through the instruction cache (OSC-action rollout, profiles/r2as_cta_tier.txt)
+  const bool use_t2 = cta_any(tier2);
+  const bool use_t1 = use_t2 || cta_any(tier1 || general);
   leg_fk_velocities(m, L, qd, k);
 
   // ---- mass matrix, bias, both factorisations (half 0: M, half 1: M + h D)

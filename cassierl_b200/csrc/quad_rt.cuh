@@ -39,6 +39,15 @@ template <typename V> QUAD_FN V shfl(V v, int src) { return __shfl_sync(0xffffff
 template <typename V> QUAD_FN V shx(V v, int m) { return __shfl_xor_sync(0xffffffffu, v, m, 4); }
 QUAD_FN void wsync() { __syncwarp(); }
 QUAD_FN bool wany(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+// any over the whole CTA (a barrier: every thread of the CTA must call it).  Used for decisions that select between large
+// unrolled code regions: the warps of a lock-step CTA share instruction-cache fills only while they run the SAME region.
+#ifndef CASSIE_QUAD_CTA_TIER
+#define CASSIE_QUAD_CTA_TIER 1
+#endif
+QUAD_FN bool cta_any(bool p) {
+  if (CASSIE_QUAD_CTA_TIER && blockDim.x > 32) return __syncthreads_or(p) != 0;
+  return wany(p);
+}
 // any / all over the four lanes of the quad only
 QUAD_FN bool qany(bool p) {
   const unsigned b = __ballot_sync(0xffffffffu, p);
@@ -107,6 +116,7 @@ QUAD_FN bool wany(bool p) {
   return r;
 }
 QUAD_FN bool qany(bool p) { return wany(p); }
+QUAD_FN bool cta_any(bool p) { return wany(p); }
 QUAD_FN unsigned wlanes(bool p) {
   Emu& e = emu();
   e.pred[emu_lane()] = p;
