@@ -760,7 +760,7 @@ QUAD_FN void quad_jacobian_control(const PlanarModel<TC>& m, const Lane ln, cons
 //   St  persistent state block (StateLayout, type T)     scratch: block used as PhysLayout (T) and CtrlLayout (double)
 //   act the action of the step (uniform over the quad)   want_op: refresh the lagged op-space state (always done in
 //   the Jacobian / OSC modes, whose controllers need the controller-model kinematics anyway)
-template <int MODE, typename T, typename TG>
+template <int MODE, bool CTA = false, typename T, typename TG>
 QUAD_FN void quad_controller_step(const PlanarModel<T>& mphys, const PlanarModel<TG>& mphys_g, const PlanarModel<TC>& mctrl,
                                   const Lane ln, SV<T> St, void* scratch, int ei, const T* act, bool want_op, QStepStats* st,
                                   OscStats* qst, unsigned* qp_set) {
@@ -794,7 +794,7 @@ QUAD_FN void quad_controller_step(const PlanarModel<T>& mphys, const PlanarModel
   }
   wsync();
   phase_sync<1>();
-  quad_physics_step(mphys, mphys_g, ln, St, Wp, st);
+  quad_physics_step<CTA>(mphys, mphys_g, ln, St, Wp, st);
 }
 
 }  // namespace quad

@@ -668,7 +668,7 @@ QUAD_FN int quad_pgs(const PlanarModel<T>& m, const Lane ln, const T (&A)[Tier<T
 // Row building + constraint solve of one tier: returns qfrc_constraint = J^T f (leg split) and the sweep count.
 // Both halves of a leg walk all of its slots (cheap), each writes the Jacobians of the slots it owns to rowJ and
 // keeps R and aref of those in registers.
-template <int TIER, typename T>
+template <int TIER, bool CTA, typename T>
 QUAD_FN void quad_constraints(const PlanarModel<T>& m, const Lane ln, SV<T> S, const LegKin<T>& k, const V8<T>& q, const V8<T>& qd,
                               const V8<T>& qs, const V8<T>& warm, T eq_rx, T eq_rz, const T (&cdist)[4][2], T sph_dist,
                               V8<T>& fc, int* sweeps_out, int* nrows_out, unsigned* mask_out) {
@@ -792,7 +792,7 @@ QUAD_FN void quad_constraints(const PlanarModel<T>& m, const Lane ln, SV<T> S, c
     CASSIE_UNROLL
     for (int c = 0; c < 8; c++) dst[c] = Jown[kk][c];
   }
-  const bool narrow = !cta_any(ncon > 1);
+  const bool narrow = !(CTA ? cta_any(ncon > 1) : wany(ncon > 1));
   wsync();
 
   // ---- b = J qacc_smooth - aref, jar = J qacc_warmstart - aref of the owned rows
@@ -875,7 +875,9 @@ QUAD_FN void quad_constraints(const PlanarModel<T>& m, const Lane ln, SV<T> S, c
 // One mj_step [EXT] (Cassie2d.cpp:92) of the env owned by this quad.  State (q, qd, warm start) and the control u
 // live in the state block St and are updated in place; S = scratch (PhysLayout).  T = working type, TG = type of the
 // position pass (double in the fp32 build: planar_engine.cuh physics_step explains why).
-template <typename T, typename TG>
+// CTA = choose the constraint tier per CTA instead of per warp (kernels whose envs spread over the tiers: env step /
+// rollout with arbitrary actions); the squatting kernels, whose envs all sit in tier 0, keep the barrier-free warp vote.
+template <bool CTA = false, typename T, typename TG>
 QUAD_FN void quad_physics_step(const PlanarModel<T>& m, const PlanarModel<TG>& mg, const Lane ln, SV<T> St, SV<T> S,
                                QStepStats* st) {
   typedef PhysLayout P;
@@ -950,8 +952,8 @@ QUAD_FN void quad_physics_step(const PlanarModel<T>& m, const PlanarModel<TG>& m
   const bool any_general = wany(general);
   // ... and per CTA where several warps run in lock step: seven warps in three different tiers would each pull their own
   // unrolled code through the instruction cache (OSC-action rollout, profiles/r2as_cta_tier.txt)
-  const bool use_t2 = cta_any(tier2);
-  const bool use_t1 = use_t2 || cta_any(tier1 || general);
+  const bool use_t2 = CTA ? cta_any(tier2) : wany(tier2);
+  const bool use_t1 = use_t2 || (CTA ? cta_any(tier1 || general) : wany(tier1 || general));
   leg_fk_velocities(m, L, qd, k);
 
   // ---- mass matrix, bias, both factorisations (half 0: M, half 1: M + h D)
@@ -996,9 +998,9 @@ QUAD_FN void quad_physics_step(const PlanarModel<T>& m, const PlanarModel<TG>& m
   V8<T> fc;
   int sweeps, nrows;
   unsigned mask;
-  if (use_t2) quad_constraints<2>(m, ln, S, k, q, qd, qs, warm, eq_rx, eq_rz, cdist, sph_dist, fc, &sweeps, &nrows, &mask);
-  else if (use_t1) quad_constraints<1>(m, ln, S, k, q, qd, qs, warm, eq_rx, eq_rz, cdist, sph_dist, fc, &sweeps, &nrows, &mask);
-  else quad_constraints<0>(m, ln, S, k, q, qd, qs, warm, eq_rx, eq_rz, cdist, sph_dist, fc, &sweeps, &nrows, &mask);
+  if (use_t2) quad_constraints<2, CTA>(m, ln, S, k, q, qd, qs, warm, eq_rx, eq_rz, cdist, sph_dist, fc, &sweeps, &nrows, &mask);
+  else if (use_t1) quad_constraints<1, CTA>(m, ln, S, k, q, qd, qs, warm, eq_rx, eq_rz, cdist, sph_dist, fc, &sweeps, &nrows, &mask);
+  else quad_constraints<0, CTA>(m, ln, S, k, q, qd, qs, warm, eq_rx, eq_rz, cdist, sph_dist, fc, &sweeps, &nrows, &mask);
 
   // ---- qacc = qacc_smooth + M^-1 qfrc_constraint, mj_Euler [EXT]: (M + h D) qacc' = qfrc_smooth + qfrc_constraint
   V8<T> x2[1] = {fc};

@@ -97,10 +97,10 @@ __device__ __forceinline__ void store_state(const BatchView<T>& v, const QuadEnv
   for (int i = qe.ln.ql; i < 12; i += 4) v.op[i * n + qe.e] = St[X::op + i];
 }
 
-template <typename T, int MODE>
+template <typename T, int MODE, bool CTA = false>
 __device__ __forceinline__ void quad_step(const ModelPair<T>& mp, const QuadEnv& qe, SV<T> St, unsigned char* wb, const T* act,
                                           bool want_op, QStepStats* st, OscStats* qs, unsigned* qps) {
-  quad_controller_step<MODE>(mp.phys, mp.phys_d, mp.ctrl_d, qe.ln, St, wb + kEnvsPerWarp * sizeof(T) * StateLayout::end, qe.ei,
+  quad_controller_step<MODE, CTA>(mp.phys, mp.phys_d, mp.ctrl_d, qe.ln, St, wb + kEnvsPerWarp * sizeof(T) * StateLayout::end, qe.ei,
                              act, want_op, st, qs, qps);
 }
 
@@ -122,7 +122,7 @@ k_qstep(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v, const T* 
   unsigned qps = v.qp_set[qe.e];
   for (int s = 0; s < n_sub; s++) {
     step_sync<MODE>();
-    quad_step<T, MODE>(mp, qe, St, wb, act, s == n_sub - 1, &st, &qs, &qps);
+    quad_step<T, MODE, true>(mp, qe, St, wb, act, s == n_sub - 1, &st, &qs, &qps);
   }
   store_state(v, qe, St);
   if (qe.active && qe.ln.ql == 0) {
@@ -194,7 +194,7 @@ k_qenv_step(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v, const
   unsigned qps = v.qp_set[qe.e];
   for (int s = 0; s < a.n_sub; s++) {
     step_sync<MODE>();
-    quad_step<T, MODE>(mp, qe, St, wb, act, s == a.n_sub - 1, &st, &qs, &qps);
+    quad_step<T, MODE, true>(mp, qe, St, wb, act, s == a.n_sub - 1, &st, &qs, &qps);
     t += 0.0005;  // cassie2d.py:122
   }
   __syncwarp();

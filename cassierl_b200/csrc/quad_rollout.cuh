@@ -121,7 +121,7 @@ k_qrollout(const __grid_constant__ ModelPair<T> mp, const BatchView<T> v, const 
     // ---- Cassie2dEnv.step(action, n)
     for (int s = 0; s < a.n_sub; s++) {
       step_sync<MODE>();
-      quad_step<T, MODE>(mp, qe, St, wb, act, s == a.n_sub - 1, &st, &qs, &qps);
+      quad_step<T, MODE, true>(mp, qe, St, wb, act, s == a.n_sub - 1, &st, &qs, &qps);
       t += 0.0005;
     }
     __syncwarp();
