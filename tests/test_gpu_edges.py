@@ -292,3 +292,41 @@ def test_random_phase_reset_on_device():
     ok = np.abs(got - exp).max(axis=1) < 1e-12
     assert ok[near == 0].all() and ok.mean() > 0.9        # rows whose index sits on a floating-point boundary may differ by one
     env.terminate(); env2.terminate()
+
+
+@pytest.mark.parametrize("mode", ["torque", "jacobian"])
+def test_joint_limit_tiers_in_flight(E, LIB, oracle, omodel, mode):
+    """Robots in the air with 3 or 4 joint limits on a leg next to standing ones (what random OSC accelerations produce,
+    rllab/envs/cassie_stand2d.py:50).  Quad engine: the 20-row tier, voted per warp (torque: one warp per CTA) or per CTA
+    (jacobian: seven lock-step warps); thread engine: its middle tier.  Every env matches the oracle facade to the fp64
+    bar, and a standing env's result does not depend on which tier its CTA mates drag it through (bit for bit)."""
+    from test_quad_host import flight_state
+    n, steps = 120, 5
+    S = np.zeros((n, 26))
+    for e in range(n):
+        if e % 3 == 0:
+            q, v = QPOS_INIT_CTOR.copy(), np.zeros(13)
+        else:
+            q, v = flight_state(omodel, 7000 + e, 3 + e % 2, 4 - (e // 2) % 3)
+        S[e] = s26(oracle, q, v)
+    act = torch.zeros(n, 6, dtype=torch.float64)
+
+    def run(states):
+        b = E.Cassie2dBatch(n, precision=64)
+        b.reset(torch.tensor(states))
+        (b.step_torque if mode == "torque" else b.step_jacobian)(act, steps)
+        out = b.get_general_state().cpu().numpy()
+        rows = b.stats().cpu().numpy()[:, 0]
+        b.close()
+        return out, rows
+
+    got, rows = run(S)
+    assert rows.max() >= 4 + 3 + 2           # the limit rows were really there
+    for e in range(0, n, 5):
+        c = oracle.Cassie2d(omodel)
+        c.reset(S[e])
+        for _ in range(steps):
+            (c.step_torque if mode == "torque" else c.step_jacobian)(np.zeros(6))
+        assert rel_err(got[e], c.general_state()) < 1e-9, e
+    alone, _ = run(np.repeat(S[0:1], n, axis=0))
+    assert np.array_equal(alone[0], got[0])
