@@ -25,6 +25,20 @@ class QuadHarness:
     def force(self, tier1=False, tier2=False, general=False):
         self.L.qh_force_tier1(int(tier1)); self.L.qh_force_tier2(int(tier2)); self.L.qh_force_general_path(int(general))
 
+    def ctrl_steps(self, mode, q, qd, warm, act, f32=False, qp_set=0):
+        """n controller steps (mode 0 torque, 1 pd, 2 jacobian, 3 osc) through quad_controller_step; same outputs as
+        conftest.Harness.ctrl_steps plus the QP partition carried from step to step"""
+        dp = ct.POINTER(ct.c_double)
+        act = np.ascontiguousarray(act, np.float64)
+        n, adim = act.shape
+        u = np.zeros((n, 6)); op = np.zeros((n, 18)); traj = np.zeros((n, 26)); mk = np.zeros(n, np.uint32)
+        qp = np.zeros((n, 2), np.int32); qs = ct.c_uint(qp_set)
+        fn = self.L.qh_ctrl_steps_f32 if f32 else self.L.qh_ctrl_steps_f64
+        fn(int(mode), n, q.ctypes.data_as(dp), qd.ctypes.data_as(dp), warm.ctypes.data_as(dp), act.ctypes.data_as(dp), adim,
+           u.ctypes.data_as(dp), op.ctypes.data_as(dp), traj.ctypes.data_as(dp), mk.ctypes.data_as(ct.POINTER(ct.c_uint)),
+           qp.ctypes.data_as(ct.POINTER(ct.c_int)), ct.byref(qs))
+        return dict(u=u, op=op, traj=traj, mask=mk, qp=qp, qp_set=qs.value)
+
     def steps(self, q, qd, warm, u, f32=False):
         dp = ct.POINTER(ct.c_double); ip = ct.POINTER(ct.c_int); up = ct.POINTER(ct.c_uint)
         u = np.ascontiguousarray(u, np.float64).reshape(-1, 6)
@@ -155,3 +169,32 @@ def test_tier2_fp32_single_step(qharness, oracle, omodel):
         assert nr[0] == 11
         worst = max(worst, rel_err(traj, ref))
     assert worst < 1e-5, worst
+
+
+# ----------------------------------------------------------------------------- the cooperative controllers
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_quad_controllers_match_oracle_facade(qharness, oracle, omodel, mode):
+    """StepPd / StepJacobian / StepOsc (Cassie2d.cpp:96-209, OSC_RBDL.cpp:114-291) as the quad engine runs them -- the task
+    loop, the 14-variable box QP and the pseudo-inverses split over four lanes -- against the oracle facade: free-running
+    fp64 trajectory, torques and lagged op-space state."""
+    from conftest import QPOS_INIT_CTOR, squat_jacobian_action, squat_osc_action
+    from test_engine_host import run_facade
+    qharness.force()
+    n = 60
+    if mode == 1:
+        rng = np.random.default_rng(7)
+        tg = QPOS_INIT_CTOR[[3, 4, 6, 8, 9, 11]] + rng.uniform(-0.1, 0.1, (n // 10, 6))
+        fn = lambda k, c: tg[k // 10]
+    elif mode == 2:
+        fn = lambda k, c: squat_jacobian_action(c.op_state(), k * 0.0005)
+    else:
+        fn = lambda k, c: squat_osc_action(c.op_state(), k * 0.0005)
+    ref, us, ops, acts, starts = run_facade(oracle, omodel, mode, fn, n)
+    q = QPOS_INIT_CTOR.copy(); qd = np.zeros(13); w = np.zeros(13)
+    out = qharness.ctrl_steps(mode, q, qd, w, acts)
+    assert rel_err(out["traj"], ref) < (1e-9 if mode != 3 else 1e-8)
+    assert rel_err(out["u"], us) < (1e-8 if mode != 3 else 1e-6)
+    assert rel_err(out["op"], ops) < 1e-8
+    if mode == 3:
+        assert out["qp"][:, 1].max() == 0          # every QP solved to optimality
+        assert np.median(out["qp"][:, 0]) == 1      # warm partition: one KKT solve per step
