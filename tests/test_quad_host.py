@@ -198,3 +198,19 @@ def test_quad_controllers_match_oracle_facade(qharness, oracle, omodel, mode):
     if mode == 3:
         assert out["qp"][:, 1].max() == 0          # every QP solved to optimality
         assert np.median(out["qp"][:, 0]) == 1      # warm partition: one KKT solve per step
+
+
+def test_quad_random_torque_trajectory_crosses_tiers(qharness, oracle, omodel):
+    """config 2's stream on the quad engine: 2000 free-running steps of random torques (the robot is thrown around and
+    ends up on the floor: joint-limit rows and body contacts come and go, so the steps alternate between the cooperative
+    tiers and the serial fallback) == oracle, contact events identical."""
+    from test_engine_host import oracle_torque_traj, random_torques
+    qharness.force()
+    n = 2000
+    u = random_torques(n, 3)
+    ref, masks, _ = oracle_torque_traj(oracle, omodel, QPOS_INIT_PY, u)
+    q = QPOS_INIT_PY.copy(); qd = np.zeros(13); w = np.zeros(13)
+    traj, nr, sw, mk = qharness.steps(q, qd, w, u)
+    assert rel_err(traj, ref) < 1e-9
+    assert np.array_equal(mk.astype(np.uint64), masks)
+    assert nr.max() > 12      # the stream left the common tier
