@@ -214,3 +214,25 @@ def test_quad_random_torque_trajectory_crosses_tiers(qharness, oracle, omodel):
     assert rel_err(traj, ref) < 1e-9
     assert np.array_equal(mk.astype(np.uint64), masks)
     assert nr.max() > 12      # the stream left the common tier
+
+
+@pytest.mark.parametrize("mode", [2, 3])
+def test_quad_controllers_fp32_single_step(qharness, oracle, omodel, mode):
+    """fp32 physics + double-precision controller (the product's fp32 build) on the quad engine, teacher-forced from the
+    oracle's states along the squatting stream: 1e-5 relative on the state (BASELINE.json tolerance)."""
+    from conftest import squat_jacobian_action, squat_osc_action
+    from test_engine_host import run_facade
+    qharness.force()
+    n = 200
+    act = squat_jacobian_action if mode == 2 else squat_osc_action
+    ref, us, ops, acts, starts = run_facade(oracle, omodel, mode, lambda k, c: act(c.op_state(), k * 0.0005), n)
+    # the QP partition is carried like the kernel carries it: from the fp64 run of the same stream
+    worst = 0.0
+    qp_set = 0
+    for k in range(0, n):
+        q, v, ws = [x.copy() for x in starts[k]]
+        o = qharness.ctrl_steps(mode, q, v, ws, acts[k:k + 1], f32=True, qp_set=qp_set)
+        qp_set = o["qp_set"]
+        if k % 4 == 0:
+            worst = max(worst, rel_err(o["traj"][0], ref[k]))
+    assert worst < 1e-5, worst
